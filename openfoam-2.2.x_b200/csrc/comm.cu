@@ -1,0 +1,216 @@
+// Host side of the multi-GPU exchange + the halo put / receive kernels.
+//
+// One process per GPU, one mesh region per GPU (the reference's decomposePar /
+// MPI model).  The only traffic between regions is
+//   * processor-patch halos: psi[faceCells] of every coupled patch, once per
+//     Amul / Tmul / residual / Gauss-Seidel sweep and per GAMG level
+//     (lduMatrixUpdateMatrixInterfaces.C:30-266, processorFvPatchScalarField.C:36-144)
+//   * 1-3 double sums per reduction (comm.cuh)
+// Both are written by the producing GPU directly into the consumer's exchange
+// window (CUDA IPC mapping, NVLink/NVSwitch P2P stores) from inside the kernels
+// that produce them; the consumer spins on an epoch flag in its own HBM.
+#include <algorithm>
+#include <cstring>
+
+#include "comm.cuh"
+#include "reduce.cuh"
+
+namespace ldu {
+
+CommDev comm_dev(const ldu_context* ctx)
+{
+    CommDev c;
+    c.rank = ctx->comm.rank;
+    c.nRanks = ctx->comm.connected ? ctx->comm.nRanks : 1;
+    c.peer = ctx->comm.d_peer;
+    c.maxInterfaces = ctx->comm.maxInterfaces;
+    c.slotStride = ctx->comm.slotStride;
+    c.timeoutCycles = 20000000000ll;  // ~10 s: fail loudly instead of hanging the GPU
+    return c;
+}
+
+struct IfaceDev {
+    int offset, n, nbrRank, nbrInterface;
+};
+
+// psi[faceCells] of every interface -> the neighbour's window, then publish the
+// epoch to every neighbour (last block).
+__global__ void __launch_bounds__(kBlock) halo_put_kernel(CommDev c, const IfaceDev* __restrict__ ifs,
+                                                           int nIfs, const int* __restrict__ ifCells,
+                                                           const double* __restrict__ psi,
+                                                           const SolverScalars* __restrict__ guard)
+{
+    if (guard && guard->done) return;
+    WindowHeader* me = win_hdr(c, c.rank);
+    const unsigned long long epoch = me->haloEpoch + 1;
+    const int par = (int)(epoch & 1ull);
+    const IfaceDev it = ifs[blockIdx.y];
+    double* dst = win_halo(c, it.nbrRank, par, it.nbrInterface);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < it.n; i += gridDim.x * kBlock)
+        dst[i] = psi[ifCells[it.offset + i]];
+    __threadfence_system();
+    __shared__ bool isLast;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&me->haloTicket, 1u);
+        isLast = (t == gridDim.x * gridDim.y - 1);
+    }
+    __syncthreads();
+    if (!isLast) return;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        me->haloTicket = 0u;
+        me->haloEpoch = epoch;
+        for (int k = 0; k < nIfs; k++) {
+            // one flag per source rank; repeated stores of the same epoch are harmless
+            st_release_sys(&win_hdr(c, ifs[k].nbrRank)->haloSeq[par][c.rank], epoch);
+        }
+    }
+}
+
+// wait for every neighbour's halo of the current epoch, then gather the window
+// slots into the matrix's concatenated receive buffer
+__global__ void __launch_bounds__(kBlock) halo_recv_kernel(CommDev c, const IfaceDev* __restrict__ ifs,
+                                                            int nIfs, double* __restrict__ recv,
+                                                            SolverScalars* __restrict__ S, bool guarded)
+{
+    if (guarded && S->done) return;
+    WindowHeader* me = win_hdr(c, c.rank);
+    const unsigned long long epoch = me->haloEpoch;
+    const int par = (int)(epoch & 1ull);
+    __shared__ bool ok;
+    if (threadIdx.x == 0) {
+        ok = true;
+        for (int k = 0; k < nIfs && ok; k++)
+            ok = wait_epoch(&me->haloSeq[par][ifs[k].nbrRank], epoch, c.timeoutCycles);
+        if (!ok) {
+            S->commError = 1;
+            S->done = 1;
+        }
+    }
+    __syncthreads();
+    if (!ok) return;
+    const IfaceDev it = ifs[blockIdx.y];
+    const double* src = win_halo(c, c.rank, par, blockIdx.y);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < it.n; i += gridDim.x * kBlock)
+        recv[it.offset + i] = ld_volatile_f64(src + i);
+}
+
+static int ensure_iface_table(ldu_matrix* m, IfaceDev** out)
+{
+    // cached in a work slot of its own (tiny)
+    static_assert(sizeof(IfaceDev) == 16, "IfaceDev layout");
+    if (!m->d_ifTable) {
+        std::vector<IfaceDev> h(m->ifs.size());
+        for (size_t i = 0; i < h.size(); i++)
+            h[i] = IfaceDev{m->ifs[i].offset, m->ifs[i].n, m->ifs[i].nbrRank, m->ifs[i].nbrInterface};
+        LDU_CUDA(cudaMalloc((void**)&m->d_ifTable, std::max<size_t>(h.size(), 1) * sizeof(IfaceDev)));
+        LDU_CUDA(cudaMemcpy(m->d_ifTable, h.data(), h.size() * sizeof(IfaceDev), cudaMemcpyHostToDevice));
+    }
+    *out = reinterpret_cast<IfaceDev*>(m->d_ifTable);
+    return LDU_OK;
+}
+
+int comm_halo_exchange(ldu_matrix* m, const double* d_psi, bool guarded)
+{
+    ldu_context* ctx = m->ctx;
+    if (!m->nIfFaces) return LDU_OK;
+    if (!ctx->comm.connected) {
+        set_error("matrix has coupled interfaces but the context has no peers (ldu_comm_connect)");
+        return LDU_ECOMM;
+    }
+    int maxN = 0;
+    for (const Interface& it : m->ifs) maxN = std::max(maxN, it.n);
+    if ((int)m->ifs.size() > ctx->comm.maxInterfaces || maxN > ctx->comm.slotStride) {
+        set_error("exchange window too small for this matrix's interfaces");
+        return LDU_ECOMM;
+    }
+    IfaceDev* tab;
+    LDU_TRY(ensure_iface_table(m, &tab));
+    const CommDev c = comm_dev(ctx);
+    dim3 grid(std::max(1, std::min(16, (maxN + kBlock - 1) / kBlock)), (unsigned)m->ifs.size());
+    halo_put_kernel<<<grid, kBlock, 0, ctx->stream>>>(c, tab, (int)m->ifs.size(), m->d_ifCells, d_psi,
+                                                      guarded ? m->d_scalars : nullptr);
+    halo_recv_kernel<<<grid, kBlock, 0, ctx->stream>>>(c, tab, (int)m->ifs.size(), m->d_recv, m->d_scalars,
+                                                       guarded);
+    count_launch(2);
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+__global__ void allreduce_kernel(CommDev c, double* vals, int n, SolverScalars* S)
+{
+    double v[kRedSlots];
+    for (int k = 0; k < kRedSlots; k++) v[k] = k < n ? vals[k] : 0.0;
+    comm_allreduce_dev<kRedSlots>(c, v, S);
+    for (int k = 0; k < n; k++) vals[k] = v[k];
+}
+
+int comm_allreduce(ldu_context* ctx, double* d_vals, int n)
+{
+    if (!ctx->comm.connected || ctx->comm.nRanks == 1) return LDU_OK;
+    if (n > kRedSlots) return LDU_EINVAL;
+    allreduce_kernel<<<1, 1, 0, ctx->stream>>>(comm_dev(ctx), d_vals, n, nullptr);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+}  // namespace ldu
+
+using namespace ldu;
+
+extern "C" {
+
+int ldu_comm_window_create(ldu_context* ctx, int rank, int nRanks, int maxInterfaces,
+                           long long maxInterfaceFaces, unsigned char* handleOut)
+{
+    if (!ctx || !handleOut || nRanks < 1 || nRanks > kMaxRanks || rank < 0 || rank >= nRanks) {
+        set_error("ldu_comm_window_create: bad argument");
+        return LDU_EINVAL;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= LDU_COMM_HANDLE_BYTES, "handle size");
+    LDU_CUDA(cudaSetDevice(ctx->device));
+    Comm& cm = ctx->comm;
+    cm.rank = rank;
+    cm.nRanks = nRanks;
+    cm.maxInterfaces = std::max(maxInterfaces, 1);
+    cm.slotStride = std::max<long long>(maxInterfaceFaces, 1);
+    cm.windowBytes = sizeof(WindowHeader) + (size_t)2 * cm.maxInterfaces * cm.slotStride * sizeof(double);
+    LDU_CUDA(cudaMalloc((void**)&cm.window, cm.windowBytes));
+    LDU_CUDA(cudaMemset(cm.window, 0, cm.windowBytes));
+    memset(handleOut, 0, LDU_COMM_HANDLE_BYTES);
+    if (nRanks > 1) {
+        cudaIpcMemHandle_t h;
+        LDU_CUDA(cudaIpcGetMemHandle(&h, cm.window));
+        memcpy(handleOut, &h, sizeof(h));
+    }
+    return LDU_OK;
+}
+
+int ldu_comm_connect(ldu_context* ctx, const unsigned char* allHandles)
+{
+    if (!ctx || !ctx->comm.window) {
+        set_error("ldu_comm_connect: create the window first");
+        return LDU_EINVAL;
+    }
+    Comm& cm = ctx->comm;
+    LDU_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < cm.nRanks; r++) {
+        if (r == cm.rank) {
+            cm.peer[r] = cm.window;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, allHandles + (size_t)r * LDU_COMM_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        LDU_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        cm.peer[r] = (unsigned char*)p;
+    }
+    LDU_CUDA(cudaMalloc((void**)&cm.d_peer, kMaxRanks * sizeof(unsigned char*)));
+    LDU_CUDA(cudaMemcpy(cm.d_peer, cm.peer, kMaxRanks * sizeof(unsigned char*), cudaMemcpyHostToDevice));
+    cm.connected = true;
+    return LDU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+// C-ABI entry points: library state, context, device memory, matrix objects.
+#include <algorithm>
+#include <cstring>
+
+#include "ldu_internal.h"
+
+namespace ldu {
+
+long long g_launches = 0;
+static thread_local std::string g_error;
+
+void set_error(const std::string& msg) { g_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    char buf[1024];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e),
+             file, line, what);
+    g_error = buf;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+        return LDU_ENODEVICE;
+    return LDU_ECUDA;
+}
+
+template <class T>
+static int upload(ldu_context* ctx, T** d, const T* h, size_t n)
+{
+    *d = nullptr;
+    LDU_CUDA(cudaMalloc((void**)d, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) LDU_CUDA(cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return LDU_OK;
+}
+
+double* work_vec(ldu_matrix* m, int idx)
+{
+    if ((int)m->work.size() <= idx) m->work.resize(idx + 1, nullptr);
+    if (!m->work[idx]) {
+        if (cudaMalloc((void**)&m->work[idx], std::max(m->nCells, 1) * sizeof(double)) != cudaSuccess)
+            return nullptr;
+    }
+    return m->work[idx];
+}
+
+int ensure_scalars(ldu_matrix* m)
+{
+    if (!m->d_scalars) {
+        LDU_CUDA(cudaMalloc((void**)&m->d_scalars, sizeof(SolverScalars)));
+        LDU_CUDA(cudaMemsetAsync(m->d_scalars, 0, sizeof(SolverScalars), m->ctx->stream));
+    }
+    if (!m->d_hist) LDU_CUDA(cudaMalloc((void**)&m->d_hist, kMaxHist * sizeof(double)));
+    return LDU_OK;
+}
+
+}  // namespace ldu
+
+using namespace ldu;
+
+extern "C" {
+
+const char* ldu_version(void) { return "ldu_b200 0.1 (sm_100a)"; }
+const char* ldu_last_error(void) { return g_error.c_str(); }
+long long ldu_launch_count(void) { return g_launches; }
+
+void ldu_controls_default(ldu_controls* c)
+{
+    memset(c, 0, sizeof(*c));
+    c->solver = LDU_SOLVER_PCG;
+    c->preconditioner = LDU_PRECOND_NONE;
+    c->smoother = LDU_SMOOTHER_GS;
+    c->maxIter = 1000;
+    c->tolerance = 1e-6;
+    c->relTol = 0.0;
+    c->nSweeps = 1;
+    c->nCellsInCoarsestLevel = 10;
+    c->mergeLevels = 1;
+    c->nPreSweeps = 0;
+    c->preSweepsLevelMultiplier = 1;
+    c->maxPreSweeps = 4;
+    c->nPostSweeps = 2;
+    c->postSweepsLevelMultiplier = 1;
+    c->maxPostSweeps = 4;
+    c->nFinestSweeps = 2;
+    c->interpolateCorrection = 0;
+    c->scaleCorrection = -1;
+    c->nVcycles = 2;
+    c->precTolerance = 1e-6;
+    c->precRelTol = 0.0;
+    c->useFaceWeights = 0;
+    c->cacheAgglomeration = 1;
+    c->checkInterval = 0;
+}
+
+int ldu_context_create(int device, void* stream, ldu_context** out)
+{
+    if (!out) return LDU_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("ldu_context_create: no CUDA device available (there is no CPU fallback)");
+        return LDU_ENODEVICE;
+    }
+    if (device < 0 || device >= count) {
+        set_error("ldu_context_create: bad device ordinal");
+        return LDU_EINVAL;
+    }
+    LDU_CUDA(cudaSetDevice(device));
+    ldu_context* ctx = new ldu_context();
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        LDU_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->ownStream = true;
+    }
+    cudaDeviceProp prop;
+    LDU_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->smCount = prop.multiProcessorCount;
+    ctx->maxBlocks = ctx->smCount * 32;
+    LDU_CUDA(cudaMalloc((void**)&ctx->d_partials, (size_t)ctx->maxBlocks * kMaxRed * sizeof(double)));
+    LDU_CUDA(cudaMalloc((void**)&ctx->d_ticket, 64));
+    LDU_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, 64, ctx->stream));
+    LDU_CUDA(cudaMalloc((void**)&ctx->d_red, kMaxRed * sizeof(double)));
+    LDU_CUDA(cudaMallocHost((void**)&ctx->h_scalars, sizeof(SolverScalars)));
+    *out = ctx;
+    return LDU_OK;
+}
+
+int ldu_context_destroy(ldu_context* ctx)
+{
+    if (!ctx) return LDU_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_partials);
+    cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_red);
+    cudaFreeHost(ctx->h_scalars);
+    for (int r = 0; r < ctx->comm.nRanks; r++) {
+        if (ctx->comm.connected && r != ctx->comm.rank && ctx->comm.peer[r])
+            cudaIpcCloseMemHandle(ctx->comm.peer[r]);
+    }
+    cudaFree(ctx->comm.d_peer);
+    cudaFree(ctx->comm.window);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return LDU_OK;
+}
+
+int ldu_context_synchronize(ldu_context* ctx)
+{
+    if (!ctx) return LDU_EINVAL;
+    LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LDU_OK;
+}
+
+void* ldu_context_stream(ldu_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int ldu_device_alloc(ldu_context* ctx, long long bytes, void** dptr)
+{
+    if (!ctx || !dptr || bytes < 0) return LDU_EINVAL;
+    LDU_CUDA(cudaSetDevice(ctx->device));
+    LDU_CUDA(cudaMalloc(dptr, (size_t)std::max<long long>(bytes, 8)));
+    return LDU_OK;
+}
+
+int ldu_device_free(ldu_context* ctx, void* dptr)
+{
+    if (!ctx) return LDU_EINVAL;
+    LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+    LDU_CUDA(cudaFree(dptr));
+    return LDU_OK;
+}
+
+int ldu_copy_h2d(ldu_context* ctx, void* dst, const void* src, long long bytes)
+{
+    if (!ctx) return LDU_EINVAL;
+    LDU_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return LDU_OK;
+}
+
+int ldu_copy_d2h(ldu_context* ctx, void* dst, const void* src, long long bytes)
+{
+    if (!ctx) return LDU_EINVAL;
+    LDU_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LDU_OK;
+}
+
+int ldu_host_alloc(long long bytes, void** hptr)
+{
+    if (!hptr) return LDU_EINVAL;
+    LDU_CUDA(cudaMallocHost(hptr, (size_t)std::max<long long>(bytes, 8)));
+    return LDU_OK;
+}
+
+int ldu_host_free(void* hptr)
+{
+    LDU_CUDA(cudaFreeHost(hptr));
+    return LDU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// matrix
+// ---------------------------------------------------------------------------
+
+// Row views of the LDU addressing (lduAddressing.C:31-169).  ownerStart is the
+// reference's; losortStart is a proper CSR pointer (the reference's version
+// leaves trailing entries at 0, lduAddressing.C:126-169, and never reads them).
+static void build_row_views(ldu_matrix* m)
+{
+    const int n = m->nCells, nf = m->nFaces;
+    m->h_ownerStart.assign(n + 1, 0);
+    m->h_losortStart.assign(n + 1, 0);
+    m->h_losort.assign(nf, 0);
+    for (int f = 0; f < nf; f++) {
+        m->h_ownerStart[m->h_l[f] + 1]++;
+        m->h_losortStart[m->h_u[f] + 1]++;
+    }
+    for (int c = 0; c < n; c++) {
+        m->h_ownerStart[c + 1] += m->h_ownerStart[c];
+        m->h_losortStart[c + 1] += m->h_losortStart[c];
+    }
+    std::vector<int> fill(m->h_losortStart.begin(), m->h_losortStart.end() - 1);
+    for (int f = 0; f < nf; f++) m->h_losort[fill[m->h_u[f]]++] = f;  // ascending f per cell
+}
+
+int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lowerAddr,
+                      const int* upperAddr, int nInterfaces, const int* ifaceSizes,
+                      const int* const* faceCells, const int* nbrRank, const int* nbrInterface,
+                      ldu_matrix** out)
+{
+    if (!ctx || !out || nCells < 0 || nFaces < 0 || (nFaces && (!lowerAddr || !upperAddr))) {
+        set_error("ldu_matrix_create: bad argument");
+        return LDU_EINVAL;
+    }
+    LDU_CUDA(cudaSetDevice(ctx->device));
+    // LDU invariants (lduAddressing.H:36-63): l < u, faces sorted by owner
+    for (int f = 0; f < nFaces; f++) {
+        const int l = lowerAddr[f], u = upperAddr[f];
+        if (l < 0 || u >= nCells || l >= u || (f && lowerAddr[f - 1] > l)) {
+            set_error("ldu_matrix_create: addressing is not in upper-triangular order");
+            return LDU_EINVAL;
+        }
+    }
+    ldu_matrix* m = new ldu_matrix();
+    m->ctx = ctx;
+    m->nCells = nCells;
+    m->nFaces = nFaces;
+    m->h_l.assign(lowerAddr, lowerAddr + nFaces);
+    m->h_u.assign(upperAddr, upperAddr + nFaces);
+    build_row_views(m);
+    std::vector<int> lowerCol(nFaces);
+    for (int k = 0; k < nFaces; k++) lowerCol[k] = m->h_l[m->h_losort[k]];
+
+    LDU_TRY(upload(ctx, &m->d_l, m->h_l.data(), nFaces));
+    LDU_TRY(upload(ctx, &m->d_u, m->h_u.data(), nFaces));
+    LDU_TRY(upload(ctx, &m->d_ownerStart, m->h_ownerStart.data(), nCells + 1));
+    LDU_TRY(upload(ctx, &m->d_losortStart, m->h_losortStart.data(), nCells + 1));
+    LDU_TRY(upload(ctx, &m->d_losort, m->h_losort.data(), nFaces));
+    LDU_TRY(upload(ctx, &m->d_lowerCol, lowerCol.data(), nFaces));
+    LDU_CUDA(cudaMalloc((void**)&m->d_diag, std::max(nCells, 1) * sizeof(double)));
+    LDU_CUDA(cudaMalloc((void**)&m->d_upper, std::max(nFaces, 1) * sizeof(double)));
+    m->d_lower = m->d_upper;
+
+    // interfaces, concatenated interface-major
+    std::vector<int> cells;
+    for (int i = 0; i < nInterfaces; i++) {
+        Interface it;
+        it.n = ifaceSizes[i];
+        it.nbrRank = nbrRank ? nbrRank[i] : 0;
+        it.nbrInterface = nbrInterface ? nbrInterface[i] : i;
+        it.offset = (int)cells.size();
+        for (int k = 0; k < it.n; k++) {
+            const int c = faceCells[i][k];
+            if (c < 0 || c >= nCells) {
+                set_error("ldu_matrix_create: interface faceCells out of range");
+                delete m;
+                return LDU_EINVAL;
+            }
+            cells.push_back(c);
+        }
+        m->ifs.push_back(it);
+    }
+    m->nIfFaces = (int)cells.size();
+    if (m->nIfFaces) {
+        LDU_TRY(upload(ctx, &m->d_ifCells, cells.data(), cells.size()));
+        LDU_CUDA(cudaMalloc((void**)&m->d_bou, cells.size() * sizeof(double)));
+        LDU_CUDA(cudaMalloc((void**)&m->d_int, cells.size() * sizeof(double)));
+        LDU_CUDA(cudaMalloc((void**)&m->d_recv, cells.size() * sizeof(double)));
+        // boundary rows: entries of one cell in (interface, face) order == the
+        // order updateMatrixInterfaces applies them in (patch loop, then face loop)
+        std::vector<int> order(cells.size());
+        for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cells[a] < cells[b]; });
+        std::vector<int> rowCell, rowStart;
+        for (size_t k = 0; k < order.size(); k++) {
+            if (k == 0 || cells[order[k]] != cells[order[k - 1]]) {
+                rowCell.push_back(cells[order[k]]);
+                rowStart.push_back((int)k);
+            }
+        }
+        rowStart.push_back((int)order.size());
+        m->nBRows = (int)rowCell.size();
+        LDU_TRY(upload(ctx, &m->d_bRowCell, rowCell.data(), rowCell.size()));
+        LDU_TRY(upload(ctx, &m->d_bRowStart, rowStart.data(), rowStart.size()));
+        LDU_TRY(upload(ctx, &m->d_bEntry, order.data(), order.size()));
+    }
+    LDU_TRY(ensure_scalars(m));
+    LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = m;
+    return LDU_OK;
+}
+
+static void free_schedule(Schedule& s)
+{
+    cudaFree(s.d_rows);
+    cudaFree(s.d_levelStart);
+    s = Schedule();
+}
+
+int ldu_matrix_destroy(ldu_matrix* m)
+{
+    if (!m) return LDU_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    gamg_free(m);
+    cudaFree(m->d_l);
+    cudaFree(m->d_u);
+    cudaFree(m->d_ownerStart);
+    cudaFree(m->d_losortStart);
+    cudaFree(m->d_losort);
+    cudaFree(m->d_lowerCol);
+    cudaFree(m->d_diag);
+    cudaFree(m->d_upper);
+    if (m->ownLower) cudaFree(m->d_lower);
+    cudaFree(m->d_ifCells);
+    cudaFree(m->d_bou);
+    cudaFree(m->d_int);
+    cudaFree(m->d_recv);
+    cudaFree(m->d_ifTable);
+    cudaFree(m->d_bRowCell);
+    cudaFree(m->d_bRowStart);
+    cudaFree(m->d_bEntry);
+    free_schedule(m->fwd);
+    free_schedule(m->bwd);
+    for (double* w : m->work) cudaFree(w);
+    cudaFree(m->d_scalars);
+    cudaFree(m->d_hist);
+    delete m;
+    return LDU_OK;
+}
+
+static int set_lower_storage(ldu_matrix* m, bool asym)
+{
+    if (asym && !m->ownLower) {
+        LDU_CUDA(cudaMalloc((void**)&m->d_lower, std::max(m->nFaces, 1) * sizeof(double)));
+        m->ownLower = true;
+    } else if (!asym && m->ownLower) {
+        LDU_CUDA(cudaStreamSynchronize(m->ctx->stream));
+        cudaFree(m->d_lower);
+        m->d_lower = m->d_upper;
+        m->ownLower = false;
+    }
+    if (!asym) m->d_lower = m->d_upper;
+    m->symmetric = !asym;
+    return LDU_OK;
+}
+
+int ldu_matrix_set_coeffs(ldu_matrix* m, const double* diag, const double* upper,
+                          const double* lower, const double* const* bouCoeffs,
+                          const double* const* intCoeffs)
+{
+    if (!m || !diag || (m->nFaces && !upper)) {
+        set_error("ldu_matrix_set_coeffs: bad argument");
+        return LDU_EINVAL;
+    }
+    cudaStream_t st = m->ctx->stream;
+    LDU_CUDA(cudaSetDevice(m->ctx->device));
+    LDU_TRY(set_lower_storage(m, lower != nullptr));
+    LDU_CUDA(cudaMemcpyAsync(m->d_diag, diag, m->nCells * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (m->nFaces) {
+        LDU_CUDA(cudaMemcpyAsync(m->d_upper, upper, m->nFaces * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (lower)
+            LDU_CUDA(cudaMemcpyAsync(m->d_lower, lower, m->nFaces * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    for (size_t i = 0; i < m->ifs.size(); i++) {
+        const Interface& it = m->ifs[i];
+        if (!it.n) continue;
+        if (!bouCoeffs || !intCoeffs || !bouCoeffs[i] || !intCoeffs[i]) {
+            set_error("ldu_matrix_set_coeffs: interface coefficients missing");
+            return LDU_EINVAL;
+        }
+        LDU_CUDA(cudaMemcpyAsync(m->d_bou + it.offset, bouCoeffs[i], it.n * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+        LDU_CUDA(cudaMemcpyAsync(m->d_int + it.offset, intCoeffs[i], it.n * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+    }
+    // the host arrays may be pageable and reused by the caller right away
+    LDU_CUDA(cudaStreamSynchronize(st));
+    m->haveCoeffs = true;
+    return LDU_OK;
+}
+
+int ldu_matrix_set_coeffs_device(ldu_matrix* m, const double* d_diag, const double* d_upper,
+                                 const double* d_lower)
+{
+    if (!m || !d_diag) return LDU_EINVAL;
+    cudaStream_t st = m->ctx->stream;
+    LDU_TRY(set_lower_storage(m, d_lower != nullptr));
+    LDU_CUDA(cudaMemcpyAsync(m->d_diag, d_diag, m->nCells * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (m->nFaces) {
+        LDU_CUDA(cudaMemcpyAsync(m->d_upper, d_upper, m->nFaces * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (d_lower)
+            LDU_CUDA(cudaMemcpyAsync(m->d_lower, d_lower, m->nFaces * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    m->haveCoeffs = true;
+    return LDU_OK;
+}
+
+int ldu_matrix_set_face_weights(ldu_matrix* m, const double* weights)
+{
+    if (!m || (m->nFaces && !weights)) return LDU_EINVAL;
+    m->h_faceWeights.assign(weights, weights + m->nFaces);
+    m->hierarchyValid = false;
+    return LDU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// Order-dependent sweeps (DIC / DILU / FDIC preconditioners and smoothers,
+// Gauss-Seidel family) as level-scheduled row kernels.
+//
+// The reference runs these as sequential face/cell loops with loop-carried
+// dependencies (DICPreconditioner.C:57-123, DILUPreconditioner.C:57-185,
+// GaussSeidelSmoother.C:125-177).  Rewritten per cell row, row c depends only on
+// rows it shares a face with: on its lower neighbours (forward sweeps) or its
+// upper neighbours (backward sweeps).  Rows are grouped by dependency depth once
+// per addressing; every depth level is one parallel step.  Inside a row the
+// terms are applied in the reference's face order with unfused multiply / add,
+// so every sweep is BIT-IDENTICAL to the sequential loop.
+#include <algorithm>
+
+#include "reduce.cuh"
+#include "sweeps.h"
+
+namespace ldu {
+
+// ---------------------------------------------------------------------------
+// schedules
+// ---------------------------------------------------------------------------
+static int upload_schedule(ldu_context* ctx, Schedule& s, const std::vector<int>& level, int nLevels)
+{
+    const int n = (int)level.size();
+    s.nLevels = nLevels;
+    s.levelStart.assign(nLevels + 1, 0);
+    for (int c = 0; c < n; c++) s.levelStart[level[c] + 1]++;
+    s.maxLevelSize = 0;
+    for (int L = 0; L < nLevels; L++) {
+        s.maxLevelSize = std::max(s.maxLevelSize, s.levelStart[L + 1]);
+        s.levelStart[L + 1] += s.levelStart[L];
+    }
+    std::vector<int> fill(s.levelStart.begin(), s.levelStart.end() - 1);
+    std::vector<int> rows(n);
+    for (int c = 0; c < n; c++) rows[fill[level[c]]++] = c;  // ascending row inside a level
+    LDU_CUDA(cudaMalloc((void**)&s.d_rows, std::max(n, 1) * sizeof(int)));
+    LDU_CUDA(cudaMalloc((void**)&s.d_levelStart, (nLevels + 1) * sizeof(int)));
+    if (n) LDU_CUDA(cudaMemcpyAsync(s.d_rows, rows.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    LDU_CUDA(cudaMemcpyAsync(s.d_levelStart, s.levelStart.data(), (nLevels + 1) * sizeof(int),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LDU_OK;
+}
+
+int build_schedules(ldu_matrix* m)
+{
+    if (m->haveSchedules) return LDU_OK;
+    const int n = m->nCells, nf = m->nFaces;
+    // forward: depth over lower neighbours.  Faces are sorted by owner, so one
+    // pass in face order sees every owner's final depth before using it.
+    std::vector<int> lev(n, 0);
+    int nLev = n ? 1 : 0;
+    for (int f = 0; f < nf; f++) {
+        const int l = m->h_l[f], u = m->h_u[f];
+        if (lev[u] < lev[l] + 1) lev[u] = lev[l] + 1;
+    }
+    for (int c = 0; c < n; c++) nLev = std::max(nLev, lev[c] + 1);
+    LDU_TRY(upload_schedule(m->ctx, m->fwd, lev, nLev));
+    // backward: depth over upper neighbours, faces in reverse order
+    std::fill(lev.begin(), lev.end(), 0);
+    nLev = n ? 1 : 0;
+    for (int f = nf - 1; f >= 0; f--) {
+        const int l = m->h_l[f], u = m->h_u[f];
+        if (lev[l] < lev[u] + 1) lev[l] = lev[u] + 1;
+    }
+    for (int c = 0; c < n; c++) nLev = std::max(nLev, lev[c] + 1);
+    LDU_TRY(upload_schedule(m->ctx, m->bwd, lev, nLev));
+    m->haveSchedules = true;
+    return LDU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernels: one level of a sweep
+// ---------------------------------------------------------------------------
+
+// forward substitution, rows of one level:
+//   w[c] = rD[c]*r[c];  for lower faces f of c (ascending): w[c] -= (rD[c]*coef[f]) * w[l[f]]
+// FDIC: (rD[c]*coef[f]) is the precomputed rDuUpper[f] (FDICPreconditioner.C:73-82)
+template <bool PRE>
+__global__ void __launch_bounds__(kBlock) fwd_level_kernel(
+    const SolverScalars* S, const int* __restrict__ rows, int nRows, const int* __restrict__ losortStart,
+    const int* __restrict__ losort, const int* __restrict__ lowerCol, const double* __restrict__ rD,
+    const double* __restrict__ coef, const double* __restrict__ r, double* __restrict__ w, bool init)
+{
+    if (S->done) return;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nRows) return;
+    const int c = rows[i];
+    const double rDc = rD[c];
+    double acc = init ? __dmul_rn(rDc, r[c]) : w[c];
+    for (int k = losortStart[c]; k < losortStart[c + 1]; k++) {
+        const int f = losort[k];
+        const double a = PRE ? coef[f] : __dmul_rn(rDc, coef[f]);
+        acc = __dsub_rn(acc, __dmul_rn(a, w[lowerCol[k]]));
+    }
+    w[c] = acc;
+}
+
+// backward substitution, rows of one level, upper faces DESCENDING:
+//   w[c] -= (rD[c]*coef[f]) * w[u[f]]
+template <bool PRE>
+__global__ void __launch_bounds__(kBlock) bwd_level_kernel(
+    const SolverScalars* S, const int* __restrict__ rows, int nRows, const int* __restrict__ ownerStart,
+    const int* __restrict__ u, const double* __restrict__ rD, const double* __restrict__ coef,
+    double* __restrict__ w)
+{
+    if (S->done) return;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nRows) return;
+    const int c = rows[i];
+    const double rDc = rD[c];
+    double acc = w[c];
+    for (int f = ownerStart[c + 1] - 1; f >= ownerStart[c]; f--) {
+        const double a = PRE ? coef[f] : __dmul_rn(rDc, coef[f]);
+        acc = __dsub_rn(acc, __dmul_rn(a, w[u[f]]));
+    }
+    w[c] = acc;
+}
+
+// calcReciprocalD, rows of one level (DICPreconditioner.C:66-74, DILU :66-75):
+//   rD[c] = diag[c];  for lower faces f (ascending): rD[c] -= upper[f]*lower[f]/rD[l[f]]
+// (the reciprocal is taken afterwards for all rows)
+__global__ void __launch_bounds__(kBlock) rD_level_kernel(
+    const int* __restrict__ rows, int nRows, const int* __restrict__ losortStart,
+    const int* __restrict__ losort, const int* __restrict__ lowerCol, const double* __restrict__ diag,
+    const double* __restrict__ upper, const double* __restrict__ lower, double* __restrict__ rD)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nRows) return;
+    const int c = rows[i];
+    double acc = diag[c];
+    for (int k = losortStart[c]; k < losortStart[c + 1]; k++) {
+        const int f = losort[k];
+        acc = __dsub_rn(acc, __ddiv_rn(__dmul_rn(upper[f], lower[f]), rD[lowerCol[k]]));
+    }
+    rD[c] = acc;
+}
+
+// Gauss-Seidel, rows of one level (GaussSeidelSmoother.C:151-176 in row form):
+//   acc = bPrime[c]
+//   lower faces (ascending): acc -= lower[f]*psi[l[f]]   (already updated this sweep)
+//   [store acc -> bLower[c] when the symmetric backward sweep needs it]
+//   upper faces (ascending): acc -= upper[f]*psi[u[f]]   (values of the previous sweep)
+//   psi[c] = acc/diag[c]
+template <bool STORE>
+__global__ void __launch_bounds__(kBlock) gs_fwd_level_kernel(
+    const SolverScalars* S, const int* __restrict__ rows, int nRows, const int* __restrict__ losortStart,
+    const int* __restrict__ losort, const int* __restrict__ lowerCol, const int* __restrict__ ownerStart,
+    const int* __restrict__ u, const double* __restrict__ diag, const double* __restrict__ upper,
+    const double* __restrict__ lower, const double* __restrict__ bPrime, double* __restrict__ bLower,
+    double* __restrict__ psi)
+{
+    if (S->done) return;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nRows) return;
+    const int c = rows[i];
+    double acc = bPrime[c];
+    for (int k = losortStart[c]; k < losortStart[c + 1]; k++)
+        acc = __dsub_rn(acc, __dmul_rn(lower[losort[k]], psi[lowerCol[k]]));
+    if (STORE) bLower[c] = acc;
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++)
+        acc = __dsub_rn(acc, __dmul_rn(upper[f], psi[u[f]]));
+    psi[c] = __ddiv_rn(acc, diag[c]);
+}
+
+// reverse sweep of symGaussSeidel (symGaussSeidelSmoother.C:180-205): bPrime[c]
+// still holds "source - interfaces - lower part" from the forward sweep.
+__global__ void __launch_bounds__(kBlock) gs_bwd_level_kernel(
+    const SolverScalars* S, const int* __restrict__ rows, int nRows, const int* __restrict__ ownerStart,
+    const int* __restrict__ u, const double* __restrict__ diag, const double* __restrict__ upper,
+    const double* __restrict__ bLower, double* __restrict__ psi)
+{
+    if (S->done) return;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nRows) return;
+    const int c = rows[i];
+    double acc = bLower[c];
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++)
+        acc = __dsub_rn(acc, __dmul_rn(upper[f], psi[u[f]]));
+    psi[c] = __ddiv_rn(acc, diag[c]);
+}
+
+#define LEVEL_LOOP(sched, body)                                             \
+    for (int L = 0; L < (sched).nLevels; L++) {                             \
+        const int start = (sched).levelStart[L];                            \
+        const int nRows = (sched).levelStart[L + 1] - start;                \
+        if (nRows <= 0) continue;                                           \
+        const int grid = (nRows + kBlock - 1) / kBlock;                     \
+        const int* rows = (sched).d_rows + start;                           \
+        body;                                                               \
+        count_launch();                                                     \
+    }
+
+int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre, const double* r,
+                  double* w, bool init)
+{
+    LDU_TRY(build_schedules(m));
+    cudaStream_t st = m->ctx->stream;
+    if (pre) {
+        LEVEL_LOOP(m->fwd, (fwd_level_kernel<true><<<grid, kBlock, 0, st>>>(
+                               m->d_scalars, rows, nRows, m->d_losortStart, m->d_losort, m->d_lowerCol, rD,
+                               coef, r, w, init)));
+    } else {
+        LEVEL_LOOP(m->fwd, (fwd_level_kernel<false><<<grid, kBlock, 0, st>>>(
+                               m->d_scalars, rows, nRows, m->d_losortStart, m->d_losort, m->d_lowerCol, rD,
+                               coef, r, w, init)));
+    }
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+int sweep_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre, double* w)
+{
+    LDU_TRY(build_schedules(m));
+    cudaStream_t st = m->ctx->stream;
+    if (pre) {
+        LEVEL_LOOP(m->bwd, (bwd_level_kernel<true><<<grid, kBlock, 0, st>>>(
+                               m->d_scalars, rows, nRows, m->d_ownerStart, m->d_u, rD, coef, w)));
+    } else {
+        LEVEL_LOOP(m->bwd, (bwd_level_kernel<false><<<grid, kBlock, 0, st>>>(
+                               m->d_scalars, rows, nRows, m->d_ownerStart, m->d_u, rD, coef, w)));
+    }
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+struct RecipMap {
+    double* rD;
+    __device__ void operator()(int i) const { rD[i] = __ddiv_rn(1.0, rD[i]); }
+};
+
+struct RecipOfMap {
+    double* rD;
+    const double* diag;
+    __device__ void operator()(int i) const { rD[i] = __ddiv_rn(1.0, diag[i]); }
+};
+
+struct FdicCoefMap {  // FDICPreconditioner.C:78-82
+    const int* l;
+    const int* u;
+    const double* rD;
+    const double* upper;
+    double* rDuUpper;
+    double* rDlUpper;
+    __device__ void operator()(int f) const
+    {
+        rDuUpper[f] = __dmul_rn(rD[u[f]], upper[f]);
+        rDlUpper[f] = __dmul_rn(rD[l[f]], upper[f]);
+    }
+};
+
+int calc_reciprocal_D(ldu_matrix* m, double* rD, bool dilu)
+{
+    LDU_TRY(build_schedules(m));
+    cudaStream_t st = m->ctx->stream;
+    const double* lower = dilu ? m->d_lower : m->d_upper;  // DIC: upper*upper (DICPreconditioner.C:73)
+    LEVEL_LOOP(m->fwd, (rD_level_kernel<<<grid, kBlock, 0, st>>>(rows, nRows, m->d_losortStart, m->d_losort,
+                                                                   m->d_lowerCol, m->d_diag, m->d_upper,
+                                                                   lower, rD)));
+    LDU_CUDA(cudaGetLastError());
+    return launch_map<false>(m, m->nCells, RecipMap{rD});
+}
+
+int calc_reciprocal_diag(ldu_matrix* m, double* rD)
+{
+    return launch_map<false>(m, m->nCells, RecipOfMap{rD, m->d_diag});
+}
+
+int calc_fdic_coeffs(ldu_matrix* m, const double* rD, double* rDuUpper, double* rDlUpper)
+{
+    return launch_map<false>(m, m->nFaces, FdicCoefMap{m->d_l, m->d_u, rD, m->d_upper, rDuUpper, rDlUpper});
+}
+
+int gs_sweep(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, bool sym)
+{
+    LDU_TRY(build_schedules(m));
+    cudaStream_t st = m->ctx->stream;
+    if (sym) {
+        LEVEL_LOOP(m->fwd, (gs_fwd_level_kernel<true><<<grid, kBlock, 0, st>>>(
+                               m->d_scalars, rows, nRows, m->d_losortStart, m->d_losort, m->d_lowerCol,
+                               m->d_ownerStart, m->d_u, m->d_diag, m->d_upper, m->d_lower, bPrime, bLower,
+                               psi)));
+        LEVEL_LOOP(m->bwd, (gs_bwd_level_kernel<<<grid, kBlock, 0, st>>>(
+                               m->d_scalars, rows, nRows, m->d_ownerStart, m->d_u, m->d_diag, m->d_upper,
+                               bLower, psi)));
+    } else {
+        LEVEL_LOOP(m->fwd, (gs_fwd_level_kernel<false><<<grid, kBlock, 0, st>>>(
+                               m->d_scalars, rows, nRows, m->d_losortStart, m->d_losort, m->d_lowerCol,
+                               m->d_ownerStart, m->d_u, m->d_diag, m->d_upper, m->d_lower, bPrime, nullptr,
+                               psi)));
+    }
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+}  // namespace ldu

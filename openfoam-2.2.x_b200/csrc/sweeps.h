@@ -1,0 +1,51 @@
+// Level-scheduled sweep primitives (sweeps.cu) and solver building blocks.
+#pragma once
+
+#include "ldu_internal.h"
+
+namespace ldu {
+
+// w = forward substitution of r (init) or of w itself; coef per face, multiplied
+// by rD[row] unless `pre` (FDIC's precomputed rDuUpper)
+int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre, const double* r,
+                  double* w, bool init);
+int sweep_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre, double* w);
+int calc_reciprocal_D(ldu_matrix* m, double* rD, bool dilu);
+int calc_reciprocal_diag(ldu_matrix* m, double* rD);
+int calc_fdic_coeffs(ldu_matrix* m, const double* rD, double* rDuUpper, double* rDlUpper);
+int gs_sweep(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, bool sym);
+
+// work-vector slots of a matrix (cell-sized scratch, allocated on first use)
+enum {
+    W_PA = 0, W_WA, W_RA, W_PT, W_WT, W_RT, W_RD, W_TMP, W_BPRIME, W_BLOWER,
+    W_APSI, W_CORR, W_RES, W_SRD, W_STMP, W_PSI, W_SRC, W_OUT, W_PRECOND_A, W_PRECOND_B,
+    W_COUNT
+};
+
+struct Precond {
+    int kind = LDU_PRECOND_NONE;
+    double* rD = nullptr;
+    double* rDuUpper = nullptr;   // FDIC, face-sized (owned)
+    double* rDlUpper = nullptr;
+};
+
+int precond_setup(ldu_matrix* m, int kind, Precond& p, int rDSlot);
+void precond_release(Precond& p);
+int precond_apply(ldu_matrix* m, const Precond& p, double* wA, const double* rA, bool transpose);
+
+struct Smoother {
+    int kind = LDU_SMOOTHER_GS;
+    Precond dic;   // DIC / DILU / FDIC part
+};
+
+int smoother_setup(ldu_matrix* m, int kind, Smoother& s);
+void smoother_release(Smoother& s);
+int smoother_apply(ldu_matrix* m, const Smoother& s, double* psi, const double* source, int nSweeps);
+
+int init_scalars(ldu_matrix* m, const ldu_controls* c);
+int read_scalars(ldu_matrix* m, SolverScalars* out);
+// wA = A psi; rA = source - wA; normFactor; initial residual; convergence test
+int solve_prologue(ldu_matrix* m, double* psi, const double* source, double* wA, double* rA, double* tmp);
+int fetch_performance(ldu_matrix* m, ldu_solver_performance* perf);
+
+}  // namespace ldu

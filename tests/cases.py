@@ -1,0 +1,84 @@
+"""Shared case tables: the systems and solver dictionaries the oracle is pinned on
+(against the compiled reference and the golden fixtures) and the GPU is checked on."""
+from ldub200 import meshes
+
+SYSTEMS = {
+    "cavity20x20": dict(nx=20, ny=20, nz=1),
+    "box12_var": dict(nx=12, ny=12, nz=12, variable=True),
+    "box9x7x5_dirichlet": dict(nx=9, ny=7, nz=5, variable=True, dirichlet=True),
+    "line50": dict(nx=50, ny=1, nz=1),
+    "asym10": dict(nx=10, ny=10, nz=10, variable=True, asym=0.3),
+    "single": dict(nx=1, ny=1, nz=1, dirichlet=True),
+}
+
+
+def system(name):
+    return meshes.laplacian_system(**SYSTEMS[name])
+
+
+_GAMG = dict(solver="GAMG", smoother="GaussSeidel", nCellsInCoarsestLevel=10, mergeLevels=1,
+             cacheAgglomeration=False)
+
+# (system, controls)
+SOLVES = [
+    ("cavity20x20", dict(solver="PCG", preconditioner="DIC", tolerance=1e-6, relTol=0)),
+    ("cavity20x20", dict(solver="PCG", preconditioner="DIC", tolerance=1e-10, relTol=0)),
+    ("cavity20x20", dict(solver="PCG", preconditioner="diagonal", tolerance=1e-6, relTol=0)),
+    ("cavity20x20", dict(solver="PCG", preconditioner="none", tolerance=1e-6, relTol=0)),
+    ("cavity20x20", dict(solver="PCG", preconditioner="FDIC", tolerance=1e-8, relTol=0)),
+    ("box12_var", dict(solver="PCG", preconditioner="DIC", tolerance=1e-9, relTol=0)),
+    ("box12_var", dict(solver="PCG", preconditioner="DIC", tolerance=0, relTol=0, maxIter=10)),
+    ("box9x7x5_dirichlet", dict(solver="PCG", preconditioner="diagonal", tolerance=1e-8, relTol=0.001)),
+    ("asym10", dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)),
+    ("asym10", dict(solver="PBiCG", preconditioner="diagonal", tolerance=1e-8, relTol=0)),
+    ("asym10", dict(solver="smoothSolver", smoother="GaussSeidel", nSweeps=2, tolerance=1e-7, relTol=0)),
+    ("cavity20x20", dict(solver="smoothSolver", smoother="symGaussSeidel", nSweeps=1, tolerance=1e-4,
+                         relTol=0, maxIter=200)),
+    ("box12_var", dict(solver="smoothSolver", smoother="DICGaussSeidel", nSweeps=1, tolerance=1e-6, relTol=0)),
+    ("box12_var", dict(solver="smoothSolver", smoother="GaussSeidel", nSweeps=-4)),
+    ("asym10", dict(solver="smoothSolver", smoother="DILUGaussSeidel", nSweeps=2, tolerance=1e-7, relTol=0)),
+    ("line50", dict(solver="PCG", preconditioner="DIC", tolerance=1e-12, relTol=0)),
+]
+
+GAMG_SOLVES = [
+    ("cavity20x20", dict(_GAMG, agglomerator="algebraicPair", tolerance=1e-8, relTol=0)),
+    ("cavity20x20", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-7, relTol=0.01)),
+    ("box12_var", dict(_GAMG, agglomerator="faceAreaPair", mergeLevels=2, tolerance=1e-8, relTol=0, nPreSweeps=1)),
+    ("box12_var", dict(_GAMG, smoother="DIC", agglomerator="algebraicPair", nCellsInCoarsestLevel=4,
+                       tolerance=1e-8, relTol=0, interpolateCorrection=True)),
+    ("box9x7x5_dirichlet", dict(_GAMG, smoother="symGaussSeidel", agglomerator="faceAreaPair",
+                                nCellsInCoarsestLevel=20, mergeLevels=3, tolerance=1e-9, relTol=0)),
+    ("asym10", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0)),
+    ("asym10", dict(_GAMG, smoother="DILU", agglomerator="algebraicPair", tolerance=1e-8, relTol=0, nPreSweeps=2)),
+    ("box12_var", dict(solver="PCG", tolerance=1e-9, relTol=0,
+                       preconditioner=dict(preconditioner="GAMG", smoother="GaussSeidel",
+                                           agglomerator="faceAreaPair", nCellsInCoarsestLevel=10,
+                                           mergeLevels=1, cacheAgglomeration=False, tolerance=1e-5,
+                                           relTol=0, nVcycles=2))),
+]
+
+PRECONDITIONERS = ["none", "diagonal", "DIC", "FDIC", "DILU"]
+SMOOTHERS = ["GaussSeidel", "symGaussSeidel", "DIC", "DILU", "FDIC", "DICGaussSeidel",
+             "DILUGaussSeidel", "nonBlockingGaussSeidel"]
+SYMMETRIC_ONLY = {"DIC", "FDIC", "DICGaussSeidel"}
+ASYMMETRIC_ONLY = {"DILU", "DILUGaussSeidel"}
+
+
+def selectable(s, name):
+    """run-time selection tables of the reference (symMatrix / asymMatrix)"""
+    asym = s["lowerCoef"] is not None
+    return not ((asym and name in SYMMETRIC_ONLY) or (not asym and name in ASYMMETRIC_ONLY))
+
+
+def ref_controls(controls):
+    """The compiled reference has no faceAreaPair (libfiniteVolume): its driver
+    registers `weightedPair`, the same pairGAMGAgglomeration fed with the
+    problem file's face weights (oracle/ref_driver.C)."""
+    def fix(d):
+        d = dict(d)
+        if d.get("agglomerator") == "faceAreaPair":
+            d["agglomerator"] = "weightedPair"
+        if isinstance(d.get("preconditioner"), dict):
+            d["preconditioner"] = fix(d["preconditioner"])
+        return d
+    return fix(controls)

@@ -1,0 +1,75 @@
+"""Pin the CPU restatement (oracle/ldu_oracle.c) against the UNMODIFIED reference
+compiled from /root/reference (oracle/_ref, built by oracle/build_ref.py).
+Bit-for-bit: same psi, same residuals, same iteration counts.
+Skipped where oracle/_ref is absent (it travels to the GPU box prebuilt)."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+
+pytestmark = pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+
+
+@pytest.mark.parametrize("name", list(cases.SYSTEMS))
+def test_operators(name):
+    s = cases.system(name)
+    w = O.World([s])
+    x = np.random.default_rng(5).standard_normal(s["nCells"])
+    assert np.array_equal(w.amul(x)[0], O.ref_run(s, "amul", psi=x)[0])
+    assert np.array_equal(w.tmul(x)[0], O.ref_run(s, "tmul", psi=x)[0])
+    assert np.array_equal(w.sumA()[0], O.ref_run(s, "suma")[0])
+    assert np.array_equal(w.residual(x, s["source"])[0], O.ref_run(s, "residual", psi=x)[0])
+
+
+@pytest.mark.parametrize("name", ["cavity20x20", "box12_var", "asym10"])
+@pytest.mark.parametrize("pre", cases.PRECONDITIONERS)
+def test_preconditioners(name, pre):
+    s = cases.system(name)
+    if not cases.selectable(s, pre):
+        pytest.skip("not in the reference's table for this matrix type")
+    w = O.World([s])
+    assert np.array_equal(w.precondition(pre, s["source"])[0], O.ref_run(s, "precondition", pre)[0])
+    if pre == "DILU":
+        assert np.array_equal(w.precondition(pre, s["source"], True)[0],
+                              O.ref_run(s, "preconditionT", pre)[0])
+
+
+@pytest.mark.parametrize("name", ["cavity20x20", "box9x7x5_dirichlet", "asym10"])
+@pytest.mark.parametrize("sm", cases.SMOOTHERS)
+def test_smoothers(name, sm):
+    s = cases.system(name)
+    if not cases.selectable(s, sm):
+        pytest.skip("not in the reference's table for this matrix type")
+    w = O.World([s])
+    psi0 = np.random.default_rng(2).standard_normal(s["nCells"])
+    want, _ = O.ref_run(s, "smooth", O.dict_text(dict(smoother=sm)), 3, psi=psi0)
+    assert np.array_equal(w.smooth(sm, psi0, s["source"], 3)[0], want)
+
+
+@pytest.mark.parametrize("case", range(len(cases.SOLVES) + len(cases.GAMG_SOLVES)))
+def test_solves(case):
+    name, ctl = (cases.SOLVES + cases.GAMG_SOLVES)[case]
+    s = cases.system(name)
+    psi_o, perf_o = O.World([s]).solve(ctl, s["psi0"], s["source"])
+    psi_r, perf_r = O.ref_solve(s, cases.ref_controls(ctl))
+    assert perf_o["nIterations"] == perf_r["nIterations"]
+    assert perf_o["initialResidual"] == perf_r["initialResidual"]
+    assert perf_o["finalResidual"] == perf_r["finalResidual"]
+    assert perf_o["converged"] == perf_r["converged"]
+    assert np.array_equal(psi_o[0], psi_r)
+
+
+@pytest.mark.parametrize("name,merge,weights", [("cavity20x20", 1, False), ("box12_var", 1, True),
+                                                ("box12_var", 2, True), ("box9x7x5_dirichlet", 3, True),
+                                                ("asym10", 1, False)])
+def test_agglomeration(name, merge, weights):
+    s = cases.system(name)
+    ctl = dict(solver="GAMG", smoother="GaussSeidel", nCellsInCoarsestLevel=10, mergeLevels=merge,
+               agglomerator="faceAreaPair" if weights else "algebraicPair")
+    mine = O.World([s]).gamg_levels(ctl)
+    ref = O.ref_agglom(s, cases.ref_controls(ctl))
+    assert len(mine) == len(ref) and len(mine) > 0
+    for a, b in zip(mine, ref):
+        assert a["nCoarse"] == b["nCoarse"]
+        assert np.array_equal(a["restrict"], b["restrict"])
