@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""bench.py — PCG iterations/s and Amul GB/s (fp64) on the 10M-cell box (216^3).
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (reference CPU path)
+    torchrun ... bench.py --gpus N ...                       (N > 1: one rank per GPU)
+
+Workload (BASELINE.json metric / SURVEY.md §8d): icoFoam-style pressure matrix on
+a 216^3 hex box (10,077,696 cells, 30,093,120 faces): symmetric 7-point Laplacian
+as fvm::laplacian builds it, one reference cell, source sin(0.37 i), psi0 = 0,
+solved with `solver PCG; preconditioner DIC` (the cavity tutorial's p solver).
+N > 1: the same mesh split into 2x1x1 / 2x2x1 / 2x2x2 blocks, one region per GPU
+(strong scaling), processor-patch halos + scalar all-reduces between GPUs.
+
+A "step" is one solver call running exactly ITERS iterations (tolerance 0,
+maxIter ITERS-1: the reference's do/while runs maxIter+1 iterations,
+PCG.C:174-178).  value = K*ITERS / time = PCG iterations per second with all
+fields resident in HBM.  e2e is the same through the host-pointer C ABI
+(ldu_matrix_set_coeffs + ldu_solve: coefficients, source and psi cross PCIe
+every step).  roofline is the Amul kernel alone: algorithmic bytes
+(24 N + 16 F) / CUDA-event time.  Inputs (0.72 GB per Amul, >1 GB
+per iteration) exceed the 126 MB L2, so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "openfoam-2.2.x_b200"))
+sys.path.insert(0, str(ROOT))
+
+METRIC = "PCG iterations/sec (fp64, DIC) on 10M-cell box; Amul GB/s in roofline"
+UNIT = "iterations/s"
+
+
+def controls(precond, iters):
+    return dict(solver="PCG", preconditioner=precond, tolerance=0.0, relTol=0.0, maxIter=iters - 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            t = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(t[0]))
+                mx = max(mx, float(t[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- #
+# reference arm / CPU baseline: the unmodified reference compiled into oracle/_ref
+# --------------------------------------------------------------------------- #
+def reference_rate(n, precond, it_a, it_b, keep=None):
+    """Steady-state PCG iterations/s of the reference on the n^3 box (1 core: the
+    reference is single-threaded per rank and there is no MPI on this box)."""
+    from ldub200 import meshes
+    from oracle import oracle as O
+    if keep is not None and "sys" in keep:
+        s = keep["sys"]
+    else:
+        s = meshes.laplacian_system(n, n, n)
+        if keep is not None:
+            keep["sys"] = s
+    if O.ref_available():
+        _, so = O.ref_run(s, "time_iters", O.dict_text(dict(solver="PCG", preconditioner=precond)), it_a - 1, it_b - 1)
+        t = [x for x in so.splitlines() if x.startswith("ITERS")][0].split()
+        ia, ta, ib, tb = int(t[1]), float(t[2]), int(t[3]), float(t[4])
+        return (ib - ia) / (tb - ta), "reference", tb + ta
+    # restatement (oracle/ldu_oracle.c) when the compiled reference did not travel
+    w = O.World([s])
+    t0 = time.perf_counter()
+    w.solve(controls(precond, it_a), s["psi0"], s["source"])
+    t1 = time.perf_counter()
+    w.solve(controls(precond, it_b), s["psi0"], s["source"])
+    t2 = time.perf_counter()
+    return (it_b - it_a) / ((t2 - t1) - (t1 - t0)), "port", t2 - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    keep = {}
+    rates = []
+    total = args.warmup + args.steps
+    for i in range(total):
+        r, kind, _ = reference_rate(args.n, args.precond, 2, 2 + args.ref_iters, keep)
+        if i >= args.warmup:
+            rates.append(r)
+    value = float(np.mean(rates))
+    sample = (f"{args.ref_iters} steady-state iterations per step of the same {args.n}^3 system "
+              f"(two fixed-iteration solves, difference removes set-up)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ref_iters / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"box{args.n} PCG+{args.precond}, {args.n**3} cells", "precond": args.precond,
+                   "timing": "reference clockTime"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+# our arm
+# --------------------------------------------------------------------------- #
+def run_ours(args):
+    import torch
+    import ldub200
+    from ldub200 import decompose
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    ctx = ldub200.Context(local_rank, stream.cuda_stream)
+    n = args.n
+    reg = decompose.local_box_region(n, rank, world)
+    nC, nF = reg["nCells"], reg["nFaces"]
+    if world > 1:
+        max_if = max((it["faceCells"].size for it in reg["interfaces"]), default=1)
+        ctx.connect_torch_distributed(8, int(max_if))
+    ifs = [ldub200.lduInterface(it["faceCells"], it["nbrRegion"], it["nbrInterface"]) for it in reg["interfaces"]]
+    A = ldub200.lduMatrix(ctx, nC, reg["lower"], reg["upper"], ifs)
+    bou = [it["bouCoeffs"] for it in reg["interfaces"]]
+    inc = [it["intCoeffs"] for it in reg["interfaces"]]
+    A.set_coeffs(reg["diag"], reg["upperCoef"], None, bou, inc)
+    d_psi = ldub200.DeviceField(ctx, nC)
+    d_src = ldub200.DeviceField(ctx, nC, reg["source"])
+    d_tmp = ldub200.DeviceField(ctx, nC)
+    solver = ldub200.lduMatrix.solver.New("p", A, controls(args.precond, args.iters))
+
+    def timed(fn, reps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident solve --------------------------------------------------
+    def step_device():
+        d_psi.zero()
+        perf = solver.solve_device(d_psi, d_src)
+        assert perf.nIterations == args.iters, str(perf)
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ldub200.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = ldub200.launch_count() - l0
+    value = args.steps * args.iters / (ms * 1e-3)
+
+    # ---- Amul alone (roofline) ------------------------------------------------------
+    d_src2 = ldub200.DeviceField(ctx, nC, np.sin(0.11 * np.arange(nC)))
+    for _ in range(5):
+        A.Amul_device(d_tmp, d_src2)
+    amul_reps = 100
+    ms_amul = timed(lambda: A.Amul_device(d_tmp, d_src2), amul_reps) / amul_reps
+    clocks = sampler.stop() if rank == 0 else None
+    # algorithmic bytes of one Amul on this rank's region: 24 N + 16 F (+20 P halo)
+    nP = sum(it["faceCells"].size for it in reg["interfaces"])
+    amul_bytes = 24 * nC + 16 * nF + 20 * nP
+    amul_gbs = amul_bytes / (ms_amul * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    # ---- end to end through the host-pointer ABI ----------------------------------------
+    h_diag = ldub200.pinned_array(nC); h_diag[:] = reg["diag"]
+    h_upper = ldub200.pinned_array(nF); h_upper[:] = reg["upperCoef"]
+    h_src = ldub200.pinned_array(nC); h_src[:] = reg["source"]
+    h_psi = ldub200.pinned_array(nC)
+
+    def step_e2e():
+        h_psi[:] = 0.0
+        A.set_coeffs(h_diag, h_upper, None, bou, inc)
+        perf = solver.solve(h_psi, h_src)
+        assert perf.nIterations == args.iters
+
+    step_e2e()
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = e2e_steps * args.iters / dt
+    h2d = 8 * (nC + nF + nC + nC) + 16 * nP
+    d2h = 8 * nC
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"box{n} PCG+{args.precond}, {n**3} cells, {world} region(s)",
+                   "precond": args.precond, "iters_per_step": args.iters,
+                   "l2": "inputs larger than L2 (0.72 GB per Amul), no flush",
+                   "pcg_alg_bytes_per_cell_iter": 352 if args.precond == "DIC" else 208},
+        "roofline": {"bound": "hbm", "kernel": "row_kernel<0> (Amul)", "achieved": amul_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": amul_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "amul_ms": ms_amul, "alg_bytes_per_launch": amul_bytes},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    traffic_file = ROOT / "profiles" / "amul_dram_bytes.json"
+    if traffic_file.exists():
+        try:
+            line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, kind, spent = reference_rate(n, args.precond, 2, 2 + args.ref_iters)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": f"{args.ref_iters} steady-state iterations of the same {n}^3 system "
+                                              f"({spent:.1f} s of CPU work)"}
+        except Exception as e:  # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line))
+    A.destroy()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=216, help="box edge (216 -> 10,077,696 cells)")
+    ap.add_argument("--precond", default="DIC")
+    ap.add_argument("--iters", type=int, default=50, help="PCG iterations per step")
+    ap.add_argument("--ref-iters", type=int, default=8, help="reference iterations timed per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,7 @@ int ldu_device_alloc(ldu_context* ctx, long long bytes, void** dptr);
 int ldu_device_free(ldu_context* ctx, void* dptr);
 int ldu_copy_h2d(ldu_context* ctx, void* dst, const void* src, long long bytes);
 int ldu_copy_d2h(ldu_context* ctx, void* dst, const void* src, long long bytes);
+int ldu_device_memset(ldu_context* ctx, void* dptr, int byteValue, long long bytes);
 /* page-locked host staging buffers (optional, speeds up the host entry points) */
 int ldu_host_alloc(long long bytes, void** hptr);
 int ldu_host_free(void* hptr);

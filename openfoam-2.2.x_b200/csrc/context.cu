@@ -186,6 +186,13 @@ int ldu_copy_d2h(ldu_context* ctx, void* dst, const void* src, long long bytes)
     return LDU_OK;
 }
 
+int ldu_device_memset(ldu_context* ctx, void* dptr, int byteValue, long long bytes)
+{
+    if (!ctx) return LDU_EINVAL;
+    LDU_CUDA(cudaMemsetAsync(dptr, byteValue, (size_t)bytes, ctx->stream));
+    return LDU_OK;
+}
+
 int ldu_host_alloc(long long bytes, void** hptr)
 {
     if (!hptr) return LDU_EINVAL;

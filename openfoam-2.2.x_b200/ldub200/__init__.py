@@ -23,4 +23,5 @@ from .api import (  # noqa: F401
     library_path,
     launch_count,
     make_controls,
+    pinned_array,
 )

@@ -45,7 +45,7 @@ _lib = None
 ABI_SYMBOLS = [
     "ldu_version", "ldu_last_error", "ldu_launch_count", "ldu_context_create", "ldu_context_destroy",
     "ldu_context_synchronize", "ldu_context_stream", "ldu_comm_window_create", "ldu_comm_connect",
-    "ldu_device_alloc", "ldu_device_free", "ldu_copy_h2d", "ldu_copy_d2h", "ldu_host_alloc",
+    "ldu_device_alloc", "ldu_device_free", "ldu_copy_h2d", "ldu_copy_d2h", "ldu_device_memset", "ldu_host_alloc",
     "ldu_host_free", "ldu_matrix_create", "ldu_matrix_destroy", "ldu_matrix_set_coeffs",
     "ldu_matrix_set_coeffs_device", "ldu_matrix_set_face_weights", "ldu_amul", "ldu_tmul", "ldu_sumA",
     "ldu_residual", "ldu_precondition", "ldu_smooth", "ldu_solve", "ldu_amul_device", "ldu_tmul_device",
@@ -81,6 +81,7 @@ def library():
         L.ldu_device_free.argtypes = [vp, vp]
         L.ldu_copy_h2d.argtypes = [vp, vp, vp, ll]
         L.ldu_copy_d2h.argtypes = [vp, vp, vp, ll]
+        L.ldu_device_memset.argtypes = [vp, vp, i, ll]
         L.ldu_host_alloc.argtypes = [ll, C.POINTER(vp)]
         L.ldu_host_free.argtypes = [vp]
         L.ldu_matrix_create.argtypes = [vp, i, i, vp, vp, i, vp, vp, vp, vp, C.POINTER(vp)]
@@ -264,6 +265,9 @@ class DeviceField:
     def upload_async(self, host_ptr: int):
         _check(self.ctx.L.ldu_copy_h2d(self.ctx.h, self.ptr, C.c_void_p(host_ptr), self.n * 8), "ldu_copy_h2d")
 
+    def zero(self):
+        _check(self.ctx.L.ldu_device_memset(self.ctx.h, self.ptr, 0, self.n * 8), "ldu_device_memset")
+
     def download(self) -> np.ndarray:
         out = np.empty(self.n)
         _check(self.ctx.L.ldu_copy_d2h(self.ctx.h, out.ctypes.data, self.ptr, self.n * 8), "ldu_copy_d2h")
@@ -273,6 +277,17 @@ class DeviceField:
         if self.ptr:
             self.ctx.L.ldu_device_free(self.ctx.h, self.ptr)
             self.ptr = None
+
+
+def pinned_array(n: int, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (ldu_host_alloc); never freed
+    explicitly (process lifetime), meant for long-lived staging buffers."""
+    L = library()
+    p = C.c_void_p()
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    _check(L.ldu_host_alloc(nbytes, C.byref(p)), "ldu_host_alloc")
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
 
 
 class lduInterface:

@@ -282,6 +282,34 @@ int main(int argc, char* argv[])
         }
         out = psi;
     }
+    else if (op == "time_iters")
+    {
+        // steady-state cost of one solver iteration: two fixed-iteration solves
+        // (tolerance 0; maxIter a and b run a+1 and b+1 iterations, PCG.C:174-178)
+        // timed separately, the difference removes construction + prologue
+        const int a = atoi(argv[5]);
+        const int b = atoi(argv[6]);
+        double t[2];
+        int its[2];
+        for (int pass = 0; pass < 2; pass++)
+        {
+            dictionary d(dictFromText(argv[4]));
+            d.add("maxIter", pass ? b : a, true);
+            d.add("tolerance", 0.0, true);
+            d.add("relTol", 0.0, true);
+            scalarField x(psi);
+            clockTime timer;
+            solverPerformance sp = lduMatrix::solver::New
+            (
+                "p", A, bouCoeffs, intCoeffs, interfaces, d
+            )->solve(x, source);
+            t[pass] = timer.elapsedTime();
+            its[pass] = sp.nIterations();
+            printPerf(sp);
+            if (pass) out = x;
+        }
+        printf("ITERS %d %.9g %d %.9g\n", its[0], t[0], its[1], t[1]);
+    }
     else if (op == "time_amul")
     {
         const int reps = atoi(argv[4]);
