@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "ldu_internal.h"
+#include "sweeps.h"
 
 namespace ldu {
 
@@ -348,6 +349,7 @@ int ldu_matrix_destroy(ldu_matrix* m)
     cudaFree(m->d_bRowCell);
     cudaFree(m->d_bRowStart);
     cudaFree(m->d_bEntry);
+    flow_free(m);
     free_schedule(m->fwd);
     free_schedule(m->bwd);
     for (double* w : m->work) cudaFree(w);

@@ -165,6 +165,11 @@ struct ldu_matrix {
     // sweep schedules (lazy)
     ldu::Schedule fwd, bwd;
     bool haveSchedules = false;
+    // dataflow sweeps (flow.cu): level-ordered chunk tables, published {value, epoch}
+    // words and chunk counters
+    void* d_ll = nullptr;
+    void* flowDir[2] = {nullptr, nullptr};   // forward / backward tables (flow.cu)
+    int flowEpoch = 0;
     // work vectors owned by the matrix (allocated lazily, reused across solves)
     std::vector<double*> work;
     ldu::SolverScalars* d_scalars = nullptr;

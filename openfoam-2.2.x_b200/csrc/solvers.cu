@@ -487,12 +487,13 @@ static int krylov_solve(ldu_matrix* m, const ldu_controls* c, double* psi, const
     Precond pre;
     if (!useGamg) LDU_TRY(precond_setup(m, c->preconditioner, pre, W_RD));
     const bool cheap = (c->preconditioner == LDU_PRECOND_NONE || c->preconditioner == LDU_PRECOND_DIAGONAL);
-    int interval = c->checkInterval > 0 ? c->checkInterval : (cheap ? 32 : 2);
+    int interval = c->checkInterval > 0 ? c->checkInterval : (cheap ? 32 : (useGamg ? 1 : 8));
+    int enqueued = 0;   // never enqueue more than the maxIter+1 iterations the loop can run
     const double* dotPartner = bicg ? rT : rA;
 
     int rc = LDU_OK;
     for (;;) {
-        for (int it = 0; it < interval && rc == LDU_OK; it++) {
+        for (int it = 0; it < interval && rc == LDU_OK && enqueued <= c->maxIter; it++, enqueued++) {
             // wA = M^-1 rA ; wArA = <wA, rA>        (PCG.C:129-132)
             if (useGamg) {
                 rc = gamg_precondition(m, c, wA, rA);

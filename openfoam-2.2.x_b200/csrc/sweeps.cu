@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kBlock) gs_bwd_level_kernel(
 int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre, const double* r,
                   double* w, bool init)
 {
+    if (flow_enabled()) return flow_forward(m, rD, coef, pre, r, w, init);
     LDU_TRY(build_schedules(m));
     cudaStream_t st = m->ctx->stream;
     if (pre) {
@@ -211,6 +212,7 @@ int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre,
 
 int sweep_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre, double* w)
 {
+    if (flow_enabled()) return flow_backward(m, rD, coef, pre, w);
     LDU_TRY(build_schedules(m));
     cudaStream_t st = m->ctx->stream;
     if (pre) {
@@ -251,9 +253,13 @@ struct FdicCoefMap {  // FDICPreconditioner.C:78-82
 
 int calc_reciprocal_D(ldu_matrix* m, double* rD, bool dilu)
 {
+    const double* lower = dilu ? m->d_lower : m->d_upper;  // DIC: upper*upper (DICPreconditioner.C:73)
+    if (flow_enabled()) {
+        LDU_TRY(flow_rD(m, rD, m->d_upper, lower));
+        return launch_map<false>(m, m->nCells, RecipMap{rD});
+    }
     LDU_TRY(build_schedules(m));
     cudaStream_t st = m->ctx->stream;
-    const double* lower = dilu ? m->d_lower : m->d_upper;  // DIC: upper*upper (DICPreconditioner.C:73)
     LEVEL_LOOP(m->fwd, (rD_level_kernel<<<grid, kBlock, 0, st>>>(rows, nRows, m->d_losortStart, m->d_losort,
                                                                    m->d_lowerCol, m->d_diag, m->d_upper,
                                                                    lower, rD)));
@@ -273,6 +279,7 @@ int calc_fdic_coeffs(ldu_matrix* m, const double* rD, double* rDuUpper, double* 
 
 int gs_sweep(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, bool sym)
 {
+    if (flow_enabled()) return flow_gs(m, bPrime, bLower, psi, sym);
     LDU_TRY(build_schedules(m));
     cudaStream_t st = m->ctx->stream;
     if (sym) {

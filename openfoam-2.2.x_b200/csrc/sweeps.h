@@ -15,6 +15,15 @@ int calc_reciprocal_diag(ldu_matrix* m, double* rD);
 int calc_fdic_coeffs(ldu_matrix* m, const double* rD, double* rDuUpper, double* rDlUpper);
 int gs_sweep(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, bool sym);
 
+// dataflow (single persistent kernel per sweep) versions, flow.cu
+bool flow_enabled();
+void flow_free(ldu_matrix* m);
+int flow_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre, const double* r, double* w,
+                 bool init);
+int flow_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre, double* w);
+int flow_rD(ldu_matrix* m, double* rD, const double* upper, const double* lower);
+int flow_gs(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, bool sym);
+
 // work-vector slots of a matrix (cell-sized scratch, allocated on first use)
 enum {
     W_PA = 0, W_WA, W_RA, W_PT, W_WT, W_RT, W_RD, W_TMP, W_BPRIME, W_BLOWER,
