@@ -174,6 +174,17 @@ def make_controls(d: dict) -> Controls:
     return c
 
 
+def gather_handles(mine: bytes) -> bytes:
+    """All-gather the opaque exchange-window handles through torch.distributed
+    (any backend): rank-major concatenation, HANDLE_BYTES each — the layout
+    ldu_comm_connect expects."""
+    import torch.distributed as dist
+    assert len(mine) == HANDLE_BYTES
+    allh = [None] * dist.get_world_size()
+    dist.all_gather_object(allh, mine)
+    return b"".join(allh)
+
+
 class SolverPerformance:
     """SolverPerformance<scalar> (matrices/LduMatrix/LduMatrix/SolverPerformance.H:78-137)."""
 
@@ -234,9 +245,7 @@ class Context:
         import torch.distributed as dist
         rank, n = dist.get_rank(), dist.get_world_size()
         mine = self.comm_window_create(rank, n, maxInterfaces, maxInterfaceFaces)
-        allh = [None] * n
-        dist.all_gather_object(allh, mine)
-        self.comm_connect(b"".join(allh))
+        self.comm_connect(gather_handles(mine))
         dist.barrier()
 
     def close(self):

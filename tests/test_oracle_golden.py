@@ -1,0 +1,75 @@
+"""The CPU restatement against the committed outputs of the reference itself
+(tests/golden/*.npz, written by tests/golden/make_golden.py from oracle/_ref).
+Bit-for-bit.  Runs everywhere (no GPU, no /root/reference, no oracle/_ref)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.mark.parametrize("name", ["cavity20x20", "box9x7x5_dirichlet", "asym10"])
+def test_operators_preconditioners_smoothers(name):
+    g = np.load(GOLD / f"ops_{name}.npz")
+    s = cases.system(name)
+    w = O.World([s])
+    x = g["x"]
+    assert np.array_equal(w.amul(x)[0], g["amul"])
+    assert np.array_equal(w.tmul(x)[0], g["tmul"])
+    assert np.array_equal(w.sumA()[0], g["sumA"])
+    assert np.array_equal(w.residual(x, s["source"])[0], g["residual"])
+    checked = 0
+    for key in g.files:
+        if key.startswith("pre_"):
+            assert np.array_equal(w.precondition(key[4:], s["source"])[0], g[key]), key
+            checked += 1
+        elif key.startswith("preT_"):
+            assert np.array_equal(w.precondition(key[5:], s["source"], True)[0], g[key]), key
+            checked += 1
+        elif key.startswith("smooth_"):
+            assert np.array_equal(w.smooth(key[7:], x, s["source"], 2)[0], g[key]), key
+            checked += 1
+    assert checked >= 8
+
+
+@pytest.mark.parametrize("case", range(len(cases.SOLVES) + len(cases.GAMG_SOLVES)))
+def test_solves(case):
+    g = np.load(GOLD / "solves.npz")
+    name, ctl = (cases.SOLVES + cases.GAMG_SOLVES)[case]
+    s = cases.system(name)
+    psi, perf = O.World([s]).solve(ctl, s["psi0"], s["source"])
+    ref = g[f"perf_{case}"]
+    assert perf["initialResidual"] == ref[0]
+    assert perf["finalResidual"] == ref[1]
+    assert perf["nIterations"] == int(ref[2])
+    assert perf["converged"] == bool(ref[3]) and perf["singular"] == bool(ref[4])
+    assert np.array_equal(psi[0], g[f"psi_{case}"])
+
+
+def test_agglomeration():
+    g = np.load(GOLD / "agglomeration.npz")
+    for name, merge, weights in [("cavity20x20", 1, False), ("box12_var", 2, True), ("asym10", 1, False)]:
+        s = cases.system(name)
+        ctl = dict(solver="GAMG", smoother="GaussSeidel", nCellsInCoarsestLevel=10, mergeLevels=merge,
+                   agglomerator="faceAreaPair" if weights else "algebraicPair")
+        levels = O.World([s]).gamg_levels(ctl)
+        keys = [k for k in g.files if k.startswith(f"{name}_m{merge}_l")]
+        assert len(levels) == len(keys) > 0
+        for lev, L in enumerate(levels):
+            assert np.array_equal(L["restrict"], g[f"{name}_m{merge}_l{lev}"])
+
+
+def test_do_while_off_by_one():
+    """PCG runs maxIter+1 iterations, GAMG maxIter (PCG.C:174-178 vs GAMGSolverSolve.C:109-113)."""
+    s = cases.system("box12_var")
+    _, p = O.World([s]).solve(dict(solver="PCG", preconditioner="DIC", tolerance=0, relTol=0, maxIter=10),
+                              s["psi0"], s["source"])
+    assert p["nIterations"] == 11 and not p["converged"]
+    _, p = O.World([s]).solve(dict(solver="GAMG", smoother="GaussSeidel", agglomerator="faceAreaPair",
+                                   nCellsInCoarsestLevel=10, mergeLevels=1, tolerance=0, relTol=0, maxIter=3),
+                              s["psi0"], s["source"])
+    assert p["nIterations"] == 3
