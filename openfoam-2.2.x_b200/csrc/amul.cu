@@ -125,11 +125,12 @@ static int launch_rows(ldu_matrix* m, const RowView& v, double* y, const double*
     return LDU_OK;
 }
 
-int k_interfaces(ldu_matrix* m, double* result, const double* psi, int whichCoeffs, double sign,
-                 bool guarded)
+// updateMatrixInterfaces: wait for the halos started by comm_halo_put, then add
+// the coupled contribution to the boundary rows
+static int k_interfaces_finish(ldu_matrix* m, double* result, int whichCoeffs, double sign, bool guarded)
 {
     if (!m->nIfFaces) return LDU_OK;
-    LDU_TRY(comm_halo_exchange(m, psi, guarded));
+    LDU_TRY(comm_halo_recv(m, guarded));
     const double* coeff = whichCoeffs ? m->d_int : m->d_bou;
     const int grid = (m->nBRows + kBlock - 1) / kBlock;
     interface_kernel<0><<<grid, kBlock, 0, m->ctx->stream>>>(m->nBRows, m->d_bRowCell, m->d_bRowStart,
@@ -140,23 +141,35 @@ int k_interfaces(ldu_matrix* m, double* result, const double* psi, int whichCoef
     return LDU_OK;
 }
 
+int k_interfaces(ldu_matrix* m, double* result, const double* psi, int whichCoeffs, double sign,
+                 bool guarded)
+{
+    LDU_TRY(comm_halo_put(m, psi, guarded));
+    return k_interfaces_finish(m, result, whichCoeffs, sign, guarded);
+}
+
+// halo puts first, interior rows while the halos fly over NVLink, coupled rows last
+// (the reference's initMatrixInterfaces / face loop / updateMatrixInterfaces order)
 int k_amul(ldu_matrix* m, double* Apsi, const double* psi, bool transpose, bool guarded)
 {
+    LDU_TRY(comm_halo_put(m, psi, guarded));
     LDU_TRY(launch_rows<0>(m, row_view(m, transpose), Apsi, psi, nullptr, guarded));
     // Amul uses interfaceBouCoeffs, Tmul interfaceIntCoeffs (lduMatrixATmul.C:57-64,118-125)
-    return k_interfaces(m, Apsi, psi, transpose ? 1 : 0, 1.0, guarded);
+    return k_interfaces_finish(m, Apsi, transpose ? 1 : 0, 1.0, guarded);
 }
 
 int k_residual(ldu_matrix* m, double* rA, const double* psi, const double* source, bool guarded)
 {
+    LDU_TRY(comm_halo_put(m, psi, guarded));
     LDU_TRY(launch_rows<1>(m, row_view(m, false), rA, psi, source, guarded));
-    return k_interfaces(m, rA, psi, 0, -1.0, guarded);
+    return k_interfaces_finish(m, rA, 0, -1.0, guarded);
 }
 
 int k_offdiag(ldu_matrix* m, double* y, const double* x)
 {
+    LDU_TRY(comm_halo_put(m, x, false));
     LDU_TRY(launch_rows<3>(m, row_view(m, false), y, x, nullptr, false));
-    return k_interfaces(m, y, x, 0, 1.0, false);
+    return k_interfaces_finish(m, y, 0, 1.0, false);
 }
 
 int k_sumA(ldu_matrix* m, double* sumA)

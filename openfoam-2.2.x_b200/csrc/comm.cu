@@ -111,10 +111,9 @@ static int ensure_iface_table(ldu_matrix* m, IfaceDev** out)
     return LDU_OK;
 }
 
-int comm_halo_exchange(ldu_matrix* m, const double* d_psi, bool guarded)
+static int halo_grid(ldu_matrix* m, dim3& grid, IfaceDev** tab)
 {
     ldu_context* ctx = m->ctx;
-    if (!m->nIfFaces) return LDU_OK;
     if (!ctx->comm.connected) {
         set_error("matrix has coupled interfaces but the context has no peers (ldu_comm_connect)");
         return LDU_ECOMM;
@@ -125,17 +124,45 @@ int comm_halo_exchange(ldu_matrix* m, const double* d_psi, bool guarded)
         set_error("exchange window too small for this matrix's interfaces");
         return LDU_ECOMM;
     }
+    LDU_TRY(ensure_iface_table(m, tab));
+    grid = dim3(std::max(1, std::min(16, (maxN + kBlock - 1) / kBlock)), (unsigned)m->ifs.size());
+    return LDU_OK;
+}
+
+// initMatrixInterfaces (lduMatrixUpdateMatrixInterfaces.C:30-93): start the halo
+// sends.  Issued BEFORE the interior row kernel so the NVLink transfer overlaps it,
+// exactly the reference's init/update split (lduMatrixATmul.C:57-64,82-89).
+int comm_halo_put(ldu_matrix* m, const double* d_psi, bool guarded)
+{
+    if (!m->nIfFaces) return LDU_OK;
+    dim3 grid;
     IfaceDev* tab;
-    LDU_TRY(ensure_iface_table(m, &tab));
-    const CommDev c = comm_dev(ctx);
-    dim3 grid(std::max(1, std::min(16, (maxN + kBlock - 1) / kBlock)), (unsigned)m->ifs.size());
-    halo_put_kernel<<<grid, kBlock, 0, ctx->stream>>>(c, tab, (int)m->ifs.size(), m->d_ifCells, d_psi,
-                                                      guarded ? m->d_scalars : nullptr);
-    halo_recv_kernel<<<grid, kBlock, 0, ctx->stream>>>(c, tab, (int)m->ifs.size(), m->d_recv, m->d_scalars,
-                                                       guarded);
-    count_launch(2);
+    LDU_TRY(halo_grid(m, grid, &tab));
+    halo_put_kernel<<<grid, kBlock, 0, m->ctx->stream>>>(comm_dev(m->ctx), tab, (int)m->ifs.size(), m->d_ifCells,
+                                                         d_psi, guarded ? m->d_scalars : nullptr);
+    count_launch();
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;
+}
+
+// updateMatrixInterfaces, first half: wait for the neighbours' halos
+int comm_halo_recv(ldu_matrix* m, bool guarded)
+{
+    if (!m->nIfFaces) return LDU_OK;
+    dim3 grid;
+    IfaceDev* tab;
+    LDU_TRY(halo_grid(m, grid, &tab));
+    halo_recv_kernel<<<grid, kBlock, 0, m->ctx->stream>>>(comm_dev(m->ctx), tab, (int)m->ifs.size(), m->d_recv,
+                                                          m->d_scalars, guarded);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+int comm_halo_exchange(ldu_matrix* m, const double* d_psi, bool guarded)
+{
+    LDU_TRY(comm_halo_put(m, d_psi, guarded));
+    return comm_halo_recv(m, guarded);
 }
 
 __global__ void allreduce_kernel(CommDev c, double* vals, int n, SolverScalars* S)

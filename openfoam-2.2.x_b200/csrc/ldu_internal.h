@@ -236,6 +236,8 @@ int gamg_solve(ldu_matrix* m, const ldu_controls* c, double* d_psi, const double
 
 // comm.cu
 int comm_allreduce(ldu_context* ctx, double* d_vals, int n);          // in-place sum over ranks
-int comm_halo_exchange(ldu_matrix* m, const double* d_psi, bool guarded);  // fills m->d_recv
+int comm_halo_put(ldu_matrix* m, const double* d_psi, bool guarded);       // psi[faceCells] -> neighbours' windows
+int comm_halo_recv(ldu_matrix* m, bool guarded);                           // wait, fills m->d_recv
+int comm_halo_exchange(ldu_matrix* m, const double* d_psi, bool guarded);  // put + recv
 
 }  // namespace ldu

@@ -1,0 +1,71 @@
+"""The drop-in boundary with the real reference classes: an OpenFOAM-2.2.x host
+program (foam/pluginDriver, linked against the reference's own libOpenFOAM.so)
+loads foam/libgpuLduSolvers.so through dlLibraryTable and solves through
+lduMatrix::solver::New, first with the reference's CPU solver, then with the
+plug-in.  Built where /root/reference exists; the binaries travel to the GPU box."""
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+import cases
+from ldub200 import meshes
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+FOAM = ROOT / "openfoam-2.2.x_b200" / "foam"
+DRIVER, PLUGIN = FOAM / "pluginDriver", FOAM / "libgpuLduSolvers.so"
+
+
+def run_driver(sysname, controls, tmp_path, override=False):
+    if not (DRIVER.exists() and PLUGIN.exists() and O.ref_available()):
+        pytest.skip("plug-in / reference binaries not built (need /root/reference at build time)")
+    s = cases.system(sysname)
+    prob = tmp_path / "p.bin"
+    meshes.write_problem(prob, s)
+    env = dict(os.environ, WM_PROJECT_DIR=str(ROOT / "oracle" / "_ref"))
+    if override:
+        env["LDU_GPU_OVERRIDE"] = "1"
+    r = subprocess.run([str(DRIVER), str(PLUGIN), str(prob), O.dict_text(controls)], env=env,
+                       capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    m = re.search(r"RESULT iters (\d+) (\d+) final (\S+) (\S+) maxRelDiff (\S+)", r.stdout)
+    assert m, r.stdout
+    return dict(it_ref=int(m.group(1)), it_gpu=int(m.group(2)), final_ref=float(m.group(3)),
+                final_gpu=float(m.group(4)), diff=float(m.group(5)), out=r.stdout)
+
+
+@pytest.mark.parametrize("sysname,controls", [
+    ("cavity20x20", dict(solver="PCG", preconditioner="DIC", tolerance=1e-6, relTol=0)),
+    ("box12_var", dict(solver="PCG", preconditioner="diagonal", tolerance=1e-7, relTol=0)),
+    ("asym10", dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)),
+    ("asym10", dict(solver="smoothSolver", smoother="GaussSeidel", nSweeps=2, tolerance=1e-7, relTol=0)),
+    ("box12_var", dict(solver="GAMG", smoother="GaussSeidel", agglomerator="algebraicPair",
+                       nCellsInCoarsestLevel=10, mergeLevels=1, cacheAgglomeration=False,
+                       tolerance=1e-8, relTol=0)),
+])
+def test_plugin_matches_reference_solver(sysname, controls, tmp_path):
+    r = run_driver(sysname, controls, tmp_path)
+    assert r["it_ref"] == r["it_gpu"]
+    assert abs(r["final_ref"] - r["final_gpu"]) <= 1e-4 * r["final_ref"] + 1e-13
+    assert r["diff"] < 1e-7
+    # same SolverPerformance line as the reference prints (foamLog parses it)
+    ref_line = [x for x in r["out"].splitlines() if x.startswith("reference: ")][0][11:]
+    gpu_line = [x for x in r["out"].splitlines() if x.startswith("plug-in  : ")][0][11:]
+    assert ref_line.split(",")[0] == gpu_line.split(",")[0]
+
+
+def test_plugin_bit_identical_with_reference_order_sums(tmp_path):
+    ctl = dict(solver="PCG", preconditioner="DIC", tolerance=1e-10, relTol=0, referenceOrderSums=True)
+    r = run_driver("cavity20x20", ctl, tmp_path)
+    assert r["it_ref"] == r["it_gpu"] and r["final_ref"] == r["final_gpu"] and r["diff"] == 0.0
+
+
+def test_override_mode_replaces_reference_names(tmp_path):
+    """LDU_GPU_OVERRIDE=1: an unmodified fvSolution entry (`solver PCG;`) runs on the GPU."""
+    ctl = dict(solver="PCG", preconditioner="DIC", tolerance=1e-6, relTol=0)
+    r = run_driver("cavity20x20", ctl, tmp_path, override=True)
+    assert r["it_ref"] == r["it_gpu"]
