@@ -214,6 +214,69 @@ int ldu_host_free(void* hptr)
 // Row views of the LDU addressing (lduAddressing.C:31-169).  ownerStart is the
 // reference's; losortStart is a proper CSR pointer (the reference's version
 // leaves trailing entries at 0, lduAddressing.C:126-169, and never reads them).
+// Is this the addressing of a lexicographic nx*ny*nz hex box with faces listed per
+// cell in the order +i, +j, +k (blockMesh + fvMeshLduAddressing)?  Decided from the
+// owner/neighbour lists alone.
+static void detect_box(ldu_matrix* m)
+{
+    const int n = m->nCells, nf = m->nFaces;
+    m->box[0] = m->box[1] = m->box[2] = 0;
+    if (n < 1) return;
+    // distinct strides u - l, at most three: 1, nx, nx*ny
+    long long strides[3] = {0, 0, 0};
+    int ns = 0;
+    for (int f = 0; f < nf; f++) {
+        const long long d = (long long)m->h_u[f] - m->h_l[f];
+        bool seen = false;
+        for (int q = 0; q < ns; q++) seen = seen || strides[q] == d;
+        if (!seen) {
+            if (ns == 3) return;
+            strides[ns++] = d;
+        }
+    }
+    std::sort(strides, strides + ns);
+    long long nx = n, ny = 1, nz = 1;
+    if (ns >= 1 && strides[0] != 1) {
+        // no i-faces: a single column of cells in i (nx == 1) is not handled here
+        return;
+    }
+    if (ns >= 2) {
+        nx = strides[1];
+        if (n % nx) return;
+        ny = n / nx;
+    }
+    if (ns == 3) {
+        if (strides[2] % nx) return;
+        ny = strides[2] / nx;
+        if (n % (nx * ny)) return;
+        nz = n / (nx * ny);
+    }
+    if (nx * ny * nz != n) return;
+    long long expect = (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1);
+    if (expect != nf) return;
+    // every cell owns exactly the faces +i, +j, +k that exist, in that order
+    int f = 0;
+    for (long long c = 0; c < n; c++) {
+        const long long i = c % nx, j = (c / nx) % ny, k = c / (nx * ny);
+        if (i < nx - 1) {
+            if (f >= nf || m->h_l[f] != c || m->h_u[f] != c + 1) return;
+            f++;
+        }
+        if (j < ny - 1) {
+            if (f >= nf || m->h_l[f] != c || m->h_u[f] != c + nx) return;
+            f++;
+        }
+        if (k < nz - 1) {
+            if (f >= nf || m->h_l[f] != c || m->h_u[f] != c + nx * ny) return;
+            f++;
+        }
+    }
+    if (f != nf) return;
+    m->box[0] = (int)nx;
+    m->box[1] = (int)ny;
+    m->box[2] = (int)nz;
+}
+
 static void build_row_views(ldu_matrix* m)
 {
     const int n = m->nCells, nf = m->nFaces;
@@ -257,6 +320,7 @@ int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lower
     m->h_l.assign(lowerAddr, lowerAddr + nFaces);
     m->h_u.assign(upperAddr, upperAddr + nFaces);
     build_row_views(m);
+    detect_box(m);
     std::vector<int> lowerCol(nFaces);
     for (int k = 0; k < nFaces; k++) lowerCol[k] = m->h_l[m->h_losort[k]];
 
@@ -350,6 +414,7 @@ int ldu_matrix_destroy(ldu_matrix* m)
     cudaFree(m->d_bRowStart);
     cudaFree(m->d_bEntry);
     flow_free(m);
+    stencil_free(m);
     free_schedule(m->fwd);
     free_schedule(m->bwd);
     for (double* w : m->work) cudaFree(w);
@@ -407,6 +472,7 @@ int ldu_matrix_set_coeffs(ldu_matrix* m, const double* diag, const double* upper
     // the host arrays may be pageable and reused by the caller right away
     LDU_CUDA(cudaStreamSynchronize(st));
     m->haveCoeffs = true;
+    m->coefGen++;
     return LDU_OK;
 }
 
@@ -422,6 +488,7 @@ int ldu_matrix_set_coeffs_device(ldu_matrix* m, const double* d_diag, const doub
         if (d_lower)
             LDU_CUDA(cudaMemcpyAsync(m->d_lower, d_lower, m->nFaces * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
+    m->coefGen++;
     m->haveCoeffs = true;
     return LDU_OK;
 }

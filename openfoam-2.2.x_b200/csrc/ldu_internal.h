@@ -170,6 +170,12 @@ struct ldu_matrix {
     void* d_ll = nullptr;
     void* flowDir[2] = {nullptr, nullptr};   // forward / backward tables (flow.cu)
     int flowEpoch = 0;
+    // structured hex box detected from the addressing (nx, ny, nz; 0 = not a box) and
+    // the line-pipelined sweep state (stencil.cu)
+    int box[3] = {0, 0, 0};
+    void* stencil = nullptr;
+    long long coefGen = 0;    // bumped whenever diag/upper/lower change
+    long long sweepGen = 0;   // bumped whenever a reciprocal diagonal is recomputed
     // work vectors owned by the matrix (allocated lazily, reused across solves)
     std::vector<double*> work;
     ldu::SolverScalars* d_scalars = nullptr;

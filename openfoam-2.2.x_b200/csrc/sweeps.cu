@@ -194,6 +194,9 @@ __global__ void __launch_bounds__(kBlock) gs_bwd_level_kernel(
 int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre, const double* r,
                   double* w, bool init)
 {
+    // FDIC's precomputed rDuUpper[f] = rD[u[f]]*upper[f] is the product the box path
+    // forms on the fly from upper[] (FDICPreconditioner.C:78-82): same bits
+    if (stencil_enabled(m)) return stencil_forward(m, rD, pre ? m->d_upper : coef, r, w, init);
     if (flow_enabled()) return flow_forward(m, rD, coef, pre, r, w, init);
     LDU_TRY(build_schedules(m));
     cudaStream_t st = m->ctx->stream;
@@ -212,6 +215,7 @@ int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre,
 
 int sweep_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre, double* w)
 {
+    if (stencil_enabled(m)) return stencil_backward(m, rD, pre ? m->d_upper : coef, w);
     if (flow_enabled()) return flow_backward(m, rD, coef, pre, w);
     LDU_TRY(build_schedules(m));
     cudaStream_t st = m->ctx->stream;
@@ -253,6 +257,7 @@ struct FdicCoefMap {  // FDICPreconditioner.C:78-82
 
 int calc_reciprocal_D(ldu_matrix* m, double* rD, bool dilu)
 {
+    m->sweepGen++;
     const double* lower = dilu ? m->d_lower : m->d_upper;  // DIC: upper*upper (DICPreconditioner.C:73)
     if (flow_enabled()) {
         LDU_TRY(flow_rD(m, rD, m->d_upper, lower));
@@ -269,6 +274,7 @@ int calc_reciprocal_D(ldu_matrix* m, double* rD, bool dilu)
 
 int calc_reciprocal_diag(ldu_matrix* m, double* rD)
 {
+    m->sweepGen++;
     return launch_map<false>(m, m->nCells, RecipOfMap{rD, m->d_diag});
 }
 

@@ -24,6 +24,12 @@ int flow_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre,
 int flow_rD(ldu_matrix* m, double* rD, const double* upper, const double* lower);
 int flow_gs(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, bool sym);
 
+// line-pipelined sweeps for structured boxes, stencil.cu
+bool stencil_enabled(const ldu_matrix* m);
+void stencil_free(ldu_matrix* m);
+int stencil_forward(ldu_matrix* m, const double* rD, const double* coef, const double* r, double* w, bool init);
+int stencil_backward(ldu_matrix* m, const double* rD, const double* coef, double* w);
+
 // work-vector slots of a matrix (cell-sized scratch, allocated on first use)
 enum {
     W_PA = 0, W_WA, W_RA, W_PT, W_WT, W_RT, W_RD, W_TMP, W_BPRIME, W_BLOWER,

@@ -102,3 +102,29 @@ def write_problem(path, sysd, psi=None, source=None, weights=False):
         (sysd["psi0"] if psi is None else psi).astype(np.float64).tofile(fh)
         if weights:
             sysd["faceWeights"].astype(np.float64).tofile(fh)
+
+
+def scramble(sysd: dict, seed: int = 1) -> dict:
+    """Renumber the cells of a system with a random permutation and restore the
+    LDU upper-triangular face order: an unstructured-looking matrix with the
+    same spectrum (what renumberMesh / an arbitrary mesher would hand over)."""
+    rng = np.random.default_rng(seed)
+    n = sysd["nCells"]
+    perm = rng.permutation(n)                       # new index of old cell
+    lo, up = perm[sysd["lower"]], perm[sysd["upper"]]
+    flip = lo > up
+    l2, u2 = np.where(flip, up, lo), np.where(flip, lo, up)
+    uc = sysd["upperCoef"]
+    lc = sysd["lowerCoef"] if sysd["lowerCoef"] is not None else uc
+    uc2, lc2 = np.where(flip, lc, uc), np.where(flip, uc, lc)
+    order = np.lexsort((u2, l2))
+    inv = np.empty(n, dtype=np.int64)
+    inv[perm] = np.arange(n)                        # old index of new cell
+    out = dict(sysd)
+    out.update(lower=l2[order].astype(np.int32), upper=u2[order].astype(np.int32),
+               upperCoef=uc2[order].copy(),
+               lowerCoef=None if sysd["lowerCoef"] is None else lc2[order].copy(),
+               diag=sysd["diag"][inv].copy(), source=sysd["source"][inv].copy(),
+               psi0=sysd["psi0"][inv].copy(),
+               faceWeights=None if sysd.get("faceWeights") is None else sysd["faceWeights"][order].copy())
+    return out

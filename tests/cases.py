@@ -9,11 +9,20 @@ SYSTEMS = {
     "line50": dict(nx=50, ny=1, nz=1),
     "asym10": dict(nx=10, ny=10, nz=10, variable=True, asym=0.3),
     "single": dict(nx=1, ny=1, nz=1, dirichlet=True),
+    # more than one 32-line tile per plane and a ragged last tile (structured-box sweeps)
+    "box7x41x3": dict(nx=7, ny=41, nz=3, variable=True),
+    "asym5x70x2": dict(nx=5, ny=70, nz=2, variable=True, asym=0.25),
+    # randomly renumbered cells: no box structure, generic dataflow sweeps
+    "scrambled9": dict(nx=9, ny=9, nz=9, variable=True, scramble=3),
+    "scrambled_asym8": dict(nx=8, ny=8, nz=8, variable=True, asym=0.3, scramble=5),
 }
 
 
 def system(name):
-    return meshes.laplacian_system(**SYSTEMS[name])
+    kw = dict(SYSTEMS[name])
+    seed = kw.pop("scramble", None)
+    s = meshes.laplacian_system(**kw)
+    return meshes.scramble(s, seed) if seed is not None else s
 
 
 _GAMG = dict(solver="GAMG", smoother="GaussSeidel", nCellsInCoarsestLevel=10, mergeLevels=1,
@@ -38,6 +47,12 @@ SOLVES = [
     ("box12_var", dict(solver="smoothSolver", smoother="GaussSeidel", nSweeps=-4)),
     ("asym10", dict(solver="smoothSolver", smoother="DILUGaussSeidel", nSweeps=2, tolerance=1e-7, relTol=0)),
     ("line50", dict(solver="PCG", preconditioner="DIC", tolerance=1e-12, relTol=0)),
+    ("box7x41x3", dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)),
+    ("box7x41x3", dict(solver="PCG", preconditioner="FDIC", tolerance=1e-8, relTol=0)),
+    ("asym5x70x2", dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)),
+    ("scrambled9", dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)),
+    ("scrambled_asym8", dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)),
+    ("scrambled9", dict(solver="smoothSolver", smoother="symGaussSeidel", nSweeps=2, tolerance=1e-6, relTol=0)),
 ]
 
 GAMG_SOLVES = [
@@ -50,6 +65,7 @@ GAMG_SOLVES = [
                                 nCellsInCoarsestLevel=20, mergeLevels=3, tolerance=1e-9, relTol=0)),
     ("asym10", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0)),
     ("asym10", dict(_GAMG, smoother="DILU", agglomerator="algebraicPair", tolerance=1e-8, relTol=0, nPreSweeps=2)),
+    ("scrambled9", dict(_GAMG, agglomerator="algebraicPair", tolerance=1e-8, relTol=0)),
     ("box12_var", dict(solver="PCG", tolerance=1e-9, relTol=0,
                        preconditioner=dict(preconditioner="GAMG", smoother="GaussSeidel",
                                            agglomerator="faceAreaPair", nCellsInCoarsestLevel=10,

@@ -45,7 +45,7 @@ from cases import SYSTEMS
 
 @pytest.fixture(params=list(SYSTEMS))
 def system(request):
-    return request.param, meshes.laplacian_system(**SYSTEMS[request.param])
+    return request.param, cases.system(request.param)
 
 
 def test_amul_family_bit_exact(ctx, system):
@@ -112,7 +112,7 @@ SOLVES = [(n, c, _rtol(c)) for n, c in cases.SOLVES]
 def test_solves_match_oracle(ctx, case):
     import ldub200
     sysname, controls, rtol = SOLVES[case]
-    s = meshes.laplacian_system(**SYSTEMS[sysname])
+    s = cases.system(sysname)
     O = _oracle()
     w = O.World([s])
     psi_o, perf_o = w.solve(controls, s["psi0"], s["source"], hist_cap=2048)
@@ -146,7 +146,7 @@ def test_gamg_hierarchy_and_iterations(ctx, case):
     """north_star: iteration-count parity for GAMG; here also bit-exact coarse matrices."""
     import ldub200
     sysname, controls = GAMG_CASES[case]
-    s = meshes.laplacian_system(**SYSTEMS[sysname])
+    s = cases.system(sysname)
     O = _oracle()
     w = O.World([s])
     lev_o = w.gamg_levels(controls)
