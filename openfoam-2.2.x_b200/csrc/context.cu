@@ -415,6 +415,7 @@ int ldu_matrix_destroy(ldu_matrix* m)
     cudaFree(m->d_bEntry);
     flow_free(m);
     stencil_free(m);
+    stencil2_free(m);
     free_schedule(m->fwd);
     free_schedule(m->bwd);
     for (double* w : m->work) cudaFree(w);

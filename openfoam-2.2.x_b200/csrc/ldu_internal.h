@@ -174,6 +174,7 @@ struct ldu_matrix {
     // the line-pipelined sweep state (stencil.cu)
     int box[3] = {0, 0, 0};
     void* stencil = nullptr;
+    void* stencil2 = nullptr;  // plane-stacked second-generation sweeps (stencil2.cu)
     long long coefGen = 0;    // bumped whenever diag/upper/lower change
     long long sweepGen = 0;   // bumped whenever a reciprocal diagonal is recomputed
     // work vectors owned by the matrix (allocated lazily, reused across solves)

@@ -345,19 +345,14 @@ int precond_apply(ldu_matrix* m, const Precond& p, double* wA, const double* rA,
     case LDU_PRECOND_DIAGONAL:
         return launch_map<true>(m, m->nCells, ScaleMap{wA, p.rD, rA});
     case LDU_PRECOND_DIC:  // DICPreconditioner.C:87-123
-        LDU_TRY(sweep_forward(m, p.rD, m->d_upper, false, rA, wA, true));
-        return sweep_backward(m, p.rD, m->d_upper, false, wA);
+        return sweep_pair(m, p.rD, m->d_upper, m->d_upper, false, rA, wA, true);
     case LDU_PRECOND_FDIC:  // FDICPreconditioner.C:88-125
-        LDU_TRY(sweep_forward(m, p.rD, p.rDuUpper, true, rA, wA, true));
-        return sweep_backward(m, p.rD, p.rDlUpper, true, wA);
+        return sweep_pair(m, p.rD, p.rDuUpper, p.rDlUpper, true, rA, wA, true);
     case LDU_PRECOND_DILU:
-        if (!transpose) {  // DILUPreconditioner.C:88-135
-            LDU_TRY(sweep_forward(m, p.rD, m->d_lower, false, rA, wA, true));
-            return sweep_backward(m, p.rD, m->d_upper, false, wA);
-        }
+        if (!transpose)  // DILUPreconditioner.C:88-135
+            return sweep_pair(m, p.rD, m->d_lower, m->d_upper, false, rA, wA, true);
         // preconditionT: DILUPreconditioner.C:138-185
-        LDU_TRY(sweep_forward(m, p.rD, m->d_upper, false, rA, wA, true));
-        return sweep_backward(m, p.rD, m->d_lower, false, wA);
+        return sweep_pair(m, p.rD, m->d_upper, m->d_lower, false, rA, wA, true);
     }
     return LDU_EINVAL;
 }
@@ -417,16 +412,12 @@ static int dic_apply(ldu_matrix* m, const Smoother& s, double* psi, const double
     for (int sweep = 0; sweep < nSweeps; sweep++) {
         LDU_TRY(k_residual(m, rA, psi, source, true));
         LDU_TRY(launch_map<true>(m, m->nCells, MulMap{rA, p.rD}));
-        if (p.kind == LDU_PRECOND_FDIC) {
-            LDU_TRY(sweep_forward(m, p.rD, p.rDuUpper, true, nullptr, rA, false));
-            LDU_TRY(sweep_backward(m, p.rD, p.rDlUpper, true, rA));
-        } else if (p.kind == LDU_PRECOND_DILU) {
-            LDU_TRY(sweep_forward(m, p.rD, m->d_lower, false, nullptr, rA, false));
-            LDU_TRY(sweep_backward(m, p.rD, m->d_upper, false, rA));
-        } else {
-            LDU_TRY(sweep_forward(m, p.rD, m->d_upper, false, nullptr, rA, false));
-            LDU_TRY(sweep_backward(m, p.rD, m->d_upper, false, rA));
-        }
+        if (p.kind == LDU_PRECOND_FDIC)
+            LDU_TRY(sweep_pair(m, p.rD, p.rDuUpper, p.rDlUpper, true, nullptr, rA, false));
+        else if (p.kind == LDU_PRECOND_DILU)
+            LDU_TRY(sweep_pair(m, p.rD, m->d_lower, m->d_upper, false, nullptr, rA, false));
+        else
+            LDU_TRY(sweep_pair(m, p.rD, m->d_upper, m->d_upper, false, nullptr, rA, false));
         LDU_TRY(launch_map<true>(m, m->nCells, AddMap{psi, rA}));
     }
     return LDU_OK;

@@ -330,16 +330,6 @@ static void free_padded(void* user, size_t elemBytes)
     if (user) cudaFree((unsigned char*)user - (size_t)kPadRows * 32 * elemBytes);
 }
 
-bool stencil_enabled(const ldu_matrix* m)
-{
-    static int on = -1;
-    if (on < 0) {
-        const char* e = getenv("LDU_STENCIL");
-        on = (e && e[0] == '0') ? 0 : 1;
-    }
-    return on && m->box[0] > 0 && flow_enabled();
-}
-
 void stencil_free(ldu_matrix* m)
 {
     StencilState* s = reinterpret_cast<StencilState*>(m->stencil);

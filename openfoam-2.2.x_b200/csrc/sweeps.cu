@@ -196,7 +196,7 @@ int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre,
 {
     // FDIC's precomputed rDuUpper[f] = rD[u[f]]*upper[f] is the product the box path
     // forms on the fly from upper[] (FDICPreconditioner.C:78-82): same bits
-    if (stencil_enabled(m)) return stencil_forward(m, rD, pre ? m->d_upper : coef, r, w, init);
+    if (stencil_version(m) >= 1) return stencil_forward(m, rD, pre ? m->d_upper : coef, r, w, init);
     if (flow_enabled()) return flow_forward(m, rD, coef, pre, r, w, init);
     LDU_TRY(build_schedules(m));
     cudaStream_t st = m->ctx->stream;
@@ -215,7 +215,7 @@ int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre,
 
 int sweep_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre, double* w)
 {
-    if (stencil_enabled(m)) return stencil_backward(m, rD, pre ? m->d_upper : coef, w);
+    if (stencil_version(m) >= 1) return stencil_backward(m, rD, pre ? m->d_upper : coef, w);
     if (flow_enabled()) return flow_backward(m, rD, coef, pre, w);
     LDU_TRY(build_schedules(m));
     cudaStream_t st = m->ctx->stream;
@@ -228,6 +228,16 @@ int sweep_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre
     }
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;
+}
+
+int sweep_pair(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, bool pre,
+               const double* r, double* w, bool init)
+{
+    // FDIC (pre): rDuUpper/rDlUpper are the products rD*upper the box path forms itself
+    if (stencil_version(m) == 2)
+        return stencil2_apply(m, rD, pre ? m->d_upper : coefF, pre ? m->d_upper : coefB, r, w, init);
+    LDU_TRY(sweep_forward(m, rD, coefF, pre, r, w, init));
+    return sweep_backward(m, rD, coefB, pre, w);
 }
 
 struct RecipMap {

@@ -25,10 +25,18 @@ int flow_rD(ldu_matrix* m, double* rD, const double* upper, const double* lower)
 int flow_gs(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, bool sym);
 
 // line-pipelined sweeps for structured boxes, stencil.cu
-bool stencil_enabled(const ldu_matrix* m);
 void stencil_free(ldu_matrix* m);
 int stencil_forward(ldu_matrix* m, const double* rD, const double* coef, const double* r, double* w, bool init);
 int stencil_backward(ldu_matrix* m, const double* rD, const double* coef, double* w);
+// second generation (stencil2.cu): both substitutions of one application, tile layout inside
+int stencil_version(const ldu_matrix* m);   // 0 = not a box / disabled, 1 = stencil.cu, 2 = stencil2.cu
+void stencil2_free(ldu_matrix* m);
+int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, const double* r,
+                   double* w, bool init);
+
+// forward then backward substitution: w = B^-1 F^-1 (init ? rD*r : w)
+int sweep_pair(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, bool pre,
+               const double* r, double* w, bool init);
 
 // work-vector slots of a matrix (cell-sized scratch, allocated on first use)
 enum {

@@ -12,6 +12,9 @@ SYSTEMS = {
     # more than one 32-line tile per plane and a ragged last tile (structured-box sweeps)
     "box7x41x3": dict(nx=7, ny=41, nz=3, variable=True),
     "asym5x70x2": dict(nx=5, ny=70, nz=2, variable=True, asym=0.25),
+    # several stacks of k-planes and two columns (plane-stacked sweeps, stencil2.cu)
+    "box6x40x9": dict(nx=6, ny=40, nz=9, variable=True),
+    "asym4x35x13": dict(nx=4, ny=35, nz=13, variable=True, asym=0.2),
     # randomly renumbered cells: no box structure, generic dataflow sweeps
     "scrambled9": dict(nx=9, ny=9, nz=9, variable=True, scramble=3),
     "scrambled_asym8": dict(nx=8, ny=8, nz=8, variable=True, asym=0.3, scramble=5),
