@@ -13,6 +13,8 @@
 // Symmetric matrices keep a single coefficient array (lower aliases upper), so
 // the HBM traffic stays at the LDU minimum: each coefficient is fetched from
 // DRAM once and served to its second row from L2.
+#include <cstdlib>
+
 #include "reduce.cuh"
 
 namespace ldu {
@@ -22,6 +24,7 @@ struct RowView {
     const int* __restrict__ losortStart;
     const int* __restrict__ losort;
     const int* __restrict__ lowerCol;
+    const int* __restrict__ lowerPacked;   // (column << 5 | face position), see ldu_internal.h
     const int* __restrict__ u;
     const double* __restrict__ diag;
     const double* __restrict__ lowerCoef;  // coefficient applied to the lower-part entries
@@ -35,6 +38,7 @@ static RowView row_view(const ldu_matrix* m, bool transpose)
     v.losortStart = m->d_losortStart;
     v.losort = m->d_losort;
     v.lowerCol = m->d_lowerCol;
+    v.lowerPacked = m->d_lowerPacked;
     v.u = m->d_u;
     v.diag = m->d_diag;
     // Amul: Apsi[u] += lower*psi[l]; Apsi[l] += upper*psi[u]
@@ -45,7 +49,7 @@ static RowView row_view(const ldu_matrix* m, bool transpose)
 }
 
 // MODE 0: y = A x   1: y = b - A x (residual)   2: y = rowsum(A) (sumA)   3: y = (A - diag) x
-template <int MODE>
+template <int MODE, bool PACKED>
 __device__ __forceinline__ double row_apply(const RowView& v, int c, const double* __restrict__ x,
                                             const double* __restrict__ b)
 {
@@ -56,9 +60,18 @@ __device__ __forceinline__ double row_apply(const RowView& v, int c, const doubl
     else acc = 0.0;
     const int k0 = v.losortStart[c], k1 = v.losortStart[c + 1];
     for (int k = k0; k < k1; k++) {
-        const double a = v.lowerCoef[v.losort[k]];
-        if (MODE == 0 || MODE == 3) acc = __dadd_rn(acc, __dmul_rn(a, x[v.lowerCol[k]]));
-        else if (MODE == 1) acc = __dsub_rn(acc, __dmul_rn(a, x[v.lowerCol[k]]));
+        int col, face;
+        if (PACKED) {   // 4 bytes per lower entry from DRAM; ownerStart[col] is an L2 hit
+            const int w = v.lowerPacked[k];
+            col = w >> 5;
+            face = v.ownerStart[col] + (w & 31);
+        } else {
+            col = v.lowerCol[k];
+            face = v.losort[k];
+        }
+        const double a = v.lowerCoef[face];
+        if (MODE == 0 || MODE == 3) acc = __dadd_rn(acc, __dmul_rn(a, x[col]));
+        else if (MODE == 1) acc = __dsub_rn(acc, __dmul_rn(a, x[col]));
         else acc = __dadd_rn(acc, a);
     }
     const int f0 = v.ownerStart[c], f1 = v.ownerStart[c + 1];
@@ -71,7 +84,7 @@ __device__ __forceinline__ double row_apply(const RowView& v, int c, const doubl
     return acc;
 }
 
-template <int MODE>
+template <int MODE, bool PACKED>
 __global__ void __launch_bounds__(kBlock) row_kernel(int n, RowView v, double* __restrict__ y,
                                                       const double* __restrict__ x,
                                                       const double* __restrict__ b,
@@ -79,7 +92,7 @@ __global__ void __launch_bounds__(kBlock) row_kernel(int n, RowView v, double* _
 {
     if (guard && guard->done) return;
     for (int c = blockIdx.x * kBlock + threadIdx.x; c < n; c += gridDim.x * kBlock)
-        y[c] = row_apply<MODE>(v, c, x, b);
+        y[c] = row_apply<MODE, PACKED>(v, c, x, b);
 }
 
 // Interface contribution, one thread per boundary cell, entries in reference
@@ -119,7 +132,11 @@ static int launch_rows(ldu_matrix* m, const RowView& v, double* y, const double*
     long long blocks = ((long long)n + kBlock - 1) / kBlock;
     const long long cap = (long long)m->ctx->smCount * 16;
     if (blocks > cap) blocks = cap;
-    row_kernel<MODE><<<(int)blocks, kBlock, 0, m->ctx->stream>>>(n, v, y, x, b, guarded ? m->d_scalars : nullptr);
+    static const bool packedOff = getenv("LDU_AMUL_PACKED") && getenv("LDU_AMUL_PACKED")[0] == '0';
+    if (v.lowerPacked && !packedOff)
+        row_kernel<MODE, true><<<(int)blocks, kBlock, 0, m->ctx->stream>>>(n, v, y, x, b, guarded ? m->d_scalars : nullptr);
+    else
+        row_kernel<MODE, false><<<(int)blocks, kBlock, 0, m->ctx->stream>>>(n, v, y, x, b, guarded ? m->d_scalars : nullptr);
     count_launch();
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;

@@ -330,6 +330,18 @@ int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lower
     LDU_TRY(upload(ctx, &m->d_losortStart, m->h_losortStart.data(), nCells + 1));
     LDU_TRY(upload(ctx, &m->d_losort, m->h_losort.data(), nFaces));
     LDU_TRY(upload(ctx, &m->d_lowerCol, lowerCol.data(), nFaces));
+    {
+        bool fits = nCells < (1 << 26);
+        for (int c = 0; c < nCells && fits; c++) fits = m->h_ownerStart[c + 1] - m->h_ownerStart[c] <= 32;
+        if (fits && nFaces) {
+            std::vector<int> packed(nFaces);
+            for (int k = 0; k < nFaces; k++) {
+                const int f = m->h_losort[k], l = m->h_l[f];
+                packed[k] = (l << 5) | (f - m->h_ownerStart[l]);
+            }
+            LDU_TRY(upload(ctx, &m->d_lowerPacked, packed.data(), nFaces));
+        }
+    }
     LDU_CUDA(cudaMalloc((void**)&m->d_diag, std::max(nCells, 1) * sizeof(double)));
     LDU_CUDA(cudaMalloc((void**)&m->d_upper, std::max(nFaces, 1) * sizeof(double)));
     m->d_lower = m->d_upper;
@@ -402,6 +414,7 @@ int ldu_matrix_destroy(ldu_matrix* m)
     cudaFree(m->d_losortStart);
     cudaFree(m->d_losort);
     cudaFree(m->d_lowerCol);
+    cudaFree(m->d_lowerPacked);
     cudaFree(m->d_diag);
     cudaFree(m->d_upper);
     if (m->ownLower) cudaFree(m->d_lower);

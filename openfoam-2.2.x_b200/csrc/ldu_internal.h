@@ -141,6 +141,10 @@ struct ldu_matrix {
     int* d_losortStart = nullptr;  // [nCells+1] CSR of losort by neighbour (lower part of a row)
     int* d_losort = nullptr;       // [nFaces] faces sorted by upper cell
     int* d_lowerCol = nullptr;     // [nFaces] l[losort[k]]: column of the k-th lower entry
+    // k-th lower entry as ONE word: (column << 5) | position of its face among the faces the
+    // column owns, i.e. face = ownerStart[column] + (word & 31).  Null when a cell owns more
+    // than 32 faces or nCells >= 2^26 (then losort/lowerCol are used).
+    int* d_lowerPacked = nullptr;
     // host copies (schedules, agglomeration)
     std::vector<int> h_l, h_u, h_ownerStart, h_losortStart, h_losort;
     // coefficients (device)

@@ -1,33 +1,47 @@
 // Plane-stacked pipelined triangular sweeps for structured hex boxes (second generation).
 //
-// Same arithmetic and the same skewed tile layout as stencil.cu (one warp owns a
-// tile of 32 x-lines of one k-plane, lane l walks line j0+l along i skewed by l
-// steps, i-neighbour = own register, j-neighbour = one shuffle), but the three
-// things that bounded the first version are removed:
+// Same arithmetic and the same skewed tile layout as stencil.cu (one warp owns a tile of 32
+// x-lines of one k-plane, lane l walks line j0+l along i skewed by l steps, i-neighbour = own
+// register, j-neighbour = one shuffle), but what bounded the first version is removed:
 //
-//   * the k-neighbour hop.  W consecutive k-planes of the same 32-line column are
-//     stacked in ONE CTA (W compute warps); plane k hands its results to plane k+1
-//     through a shared-memory ring of {value, tag} words (a plane trails the one
-//     below it by a shared-memory latency, ~10^2 cycles) instead of a word polled
-//     in L2 (~10^3 cycles).  Only every W-th plane crosses CTAs.
-//   * natural-layout traffic in the sweep.  The vector being substituted lives in
-//     tile layout for both sweeps: every operand and the result is one coalesced
-//     256-byte row per step.  pack/unpack kernels transpose 32x32 blocks through
-//     shared memory between the natural cell order and the tile layout.
-//   * memory latency on the compute warps.  A helper warp per CTA (a) polls the
-//     {value, epoch} words published by other CTAs in global memory (the plane
-//     below the stack, the last line of the previous column) and forwards them into
-//     shared-memory rings, (b) issues cp.async.bulk.prefetch.L2 for the operand
-//     rows ~48 steps ahead of every compute warp.  The compute warps only see
-//     coalesced loads that hit L2, shared memory and registers.
+//   * the k-neighbour hop.  W consecutive k-planes of the same 32-line column are stacked in
+//     ONE CTA (W compute warps) that tick together through a named barrier: plane k hands
+//     its result to plane k+1 through shared memory, one tick later, instead of through a
+//     {value, epoch} word polled in L2 (~10^3 cycles per plane in the first version).  Only
+//     every W-th plane crosses CTAs.
+//   * natural-layout traffic in the sweep.  The vector being substituted lives in tile layout
+//     for both sweeps: every operand and the result is one coalesced 256-byte row per step.
+//     pack/unpack kernels transpose 32x32 blocks through shared memory between the natural
+//     cell order and the tile layout.
+//   * global-memory latency on the compute warps.  Operand rows stream through a cp.async ring
+//     in shared memory; a helper warp per CTA polls the words other CTAs publish in global
+//     memory (the plane below the stack, the last line of the previous column), four rows per
+//     round trip, and forwards them into tagged rings in shared memory.
 //
 // The coefficient operands are stored premultiplied, P = rD[c]*coef[f], the product the
-// reference forms first (wA[u] -= rD[u]*upper[f]*wA[l], DICPreconditioner.C:108-121),
-// so each term is one multiply and one subtract and results stay BIT-IDENTICAL to the
-// reference and to the generic dataflow path.
+// reference forms first (wA[u] -= rD[u]*upper[f]*wA[l], DICPreconditioner.C:108-121), so each
+// term is one multiply and one subtract and results stay BIT-IDENTICAL to the reference and
+// to the generic dataflow path.
 //
-// CTAs claim their (k-group, column) tile from an atomic ticket in dependency order, so
-// a CTA only ever waits on CTAs that are already running: no co-residency requirement.
+// CTAs claim their (stack, column) tile from an atomic ticket in dependency order, so a CTA
+// only ever waits on CTAs that are already running: no co-residency requirement.
+//
+// What was measured on B200 while getting here (216^3, microseconds per sweep incl. its share
+// of pack/unpack; tests/perf_sweeps.py, tests/micro/sync_latency.cu):
+//   first generation (one word in L2 per cell)                               1263
+//   stacks + per-step {value, tag} polling between planes                     595   (54 % of all
+//       instructions were polls; every plane catches up with the one below and then polls)
+//   stacks ticking through bar.sync, operands double-buffered in registers    528   (the planes
+//       reach their refill burst in different ticks, so every tick has a straggler)
+//   the same through an mbarrier (split arrive/wait)                       640-760   (an mbarrier
+//       tick costs 150-370 cycles against 40-60 for bar.sync)
+//   per-step register FIFO of operands                                        790   (loads share
+//       the warp's counting scoreboards: waiting for the oldest waits for the youngest)
+//   TMA bulk chunks + mbarrier per ring slot                                  585   (chunk
+//       boundaries of the planes fall into different ticks again)
+//   cp.async ring, uniform steps, asynchronous helper (this file)             452   (W = 6)
+// A tick still costs ~470 cycles (60-70 dependent instructions per step and plane); the
+// barrier + hand-off chain alone is 105.
 #include <algorithm>
 #include <cstdlib>
 
@@ -40,13 +54,7 @@ namespace {
 
 constexpr int kRing = 16;          // ring depth (steps) of every shared-memory hand-off
 constexpr int kD = 8;              // operand rows in flight per plane: register FIFO depth = unroll factor
-constexpr int kPad2 = 16;          // zero rows in front of / behind the tile arrays
-constexpr int kC = 4;              // steps per operand chunk (one TMA bulk copy per operand)
-constexpr int kNS = 3;             // operand chunks in flight per plane
-constexpr int kA = 2;              // ticks between a word entering shared memory and its use
-constexpr int kF = 4;              // ticks a global word is requested ahead of being forwarded
-constexpr int kPfChunk = 16;       // rows per L2 bulk prefetch (16 * 256 B = 4 KB)
-constexpr int kPfAhead = 48;       // rows the prefetch runs ahead of a compute warp
+constexpr int kPad2 = kD + 2;      // zero rows in front of / behind the tile arrays
 constexpr long long kTimeout2 = 4000000000ll;
 
 struct LLW {
@@ -87,11 +95,6 @@ __device__ __forceinline__ unsigned long long gtimer()
     return t;
 }
 
-__device__ __forceinline__ void l2_prefetch(const void* p, unsigned int bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 struct S2Args {
     SolverScalars* S;
     int guarded;
@@ -104,12 +107,11 @@ struct S2Args {
     LLW* gK;            // [nKg][nJ][steps][32]  last plane of a stack, for the next stack
     LLW* gJ;            // [nTiles][steps]       edge line of a tile, for the next column
     unsigned int* ticket;  // [0] claimed, [1] finished
-    int prefetch;
     unsigned long long* trace;   // debug (LDU_S2_TRACE): per CTA {ticket, start, first plane done, last plane done, helper loops, helper done}
 };
 
 struct Shared2 {
-    unsigned long long bar;  // the tick mbarrier
+    volatile int prog[32];   // steps completed by plane p, published every 4 steps
     volatile int abort;
     int ticket;
     int finished;
@@ -124,6 +126,20 @@ __device__ __forceinline__ bool give_up(Shared2* sh, long long& tstart)
     return __any_sync(0xffffffffu, bad);
 }
 
+__device__ __forceinline__ void s_peek_a(unsigned int addr, LLW& w)
+{
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w.lo), "=r"(w.f0), "=r"(w.hi), "=r"(w.f1)
+                 : "r"(addr)
+                 : "memory");
+}
+
+__device__ __forceinline__ void s_store_a(unsigned int addr, unsigned int lo, unsigned int hi, unsigned int tag)
+{
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
+                 : "memory");
+}
+
 __device__ __forceinline__ double lds64(unsigned int addr)
 {
     double v;
@@ -134,47 +150,6 @@ __device__ __forceinline__ double lds64(unsigned int addr)
 __device__ __forceinline__ void sts64(unsigned int addr, double v)
 {
     asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-}
-
-// The planes of a stack and the helper warp tick together through one mbarrier in shared
-// memory (one arrive per warp and tick): arriving and waiting are separate operations, so
-// a warp can arrive as soon as its result is handed off and do the rest of its step while
-// the others catch up.
-__device__ __forceinline__ void mbar_init(unsigned int bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void* src, unsigned int bytes, unsigned int bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(unsigned int bar)
-{
-    unsigned long long state;
-    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar) : "memory");
-    (void)state;
-}
-
-__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity)
-{
-    unsigned int done;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-    } while (!done);
 }
 
 __device__ __forceinline__ void cp_async8(unsigned int dst, const double* src)
@@ -193,30 +168,31 @@ struct StepOps2 {
 };
 
 // Shared memory of one CTA:
-//   kx [W][2][32]     plane p's result of its step n, slot n&1: read by plane p+1 one tick later
-//   hk [kRing][32]    helper -> first plane: results of the stack below, slot n % kRing
-//   hj [W][kRing]     helper -> edge lanes: last line of the previous column, slot n % kRing
+//   kx  [W][2][32]        plane p's result of its step n, slot n&1: read by plane p+1 one tick later
+//   hk  [kRing][32] LLW   helper -> first plane: results of the stack below, {value, tag = n + 1}
+//   hj  [W][kRing]  LLW   helper -> edge lanes: last line of the previous column, {value, tag = n + 1}
+//   ops [W][kD][4][32]    operand ring of every plane: pk, pj, pi, src rows of the next kD steps
+//   prog[W]               steps completed by plane p (flow control of the helper's rings)
 template <int W>
 struct Smem2 {
     double kx[W][2][32];
-    double hk[kRing][32];
-    double hj[W][kRing];
-    double ops[W][kNS][4][kC][32];       // operand ring of every plane: pk, pj, pi, src rows of kNS chunks
-    unsigned long long full[W][kNS];     // mbarrier per ring slot: the chunk's bytes have landed
+    LLW hk[kRing][32];
+    LLW hj[W][kRing];
+    double ops[W][kD][4][32];
     Shared2 sh;
 };
 
-// One stack of up to W planes of one column.  All warps of the CTA tick together through
-// barrier 1: in interval T (between barrier T and barrier T+1) plane p executes its step
-// n = T - p, reading what plane p-1 wrote in interval T-1.  The helper warp is part of the
-// barrier: the words of other CTAs that interval T reads were put into shared memory kA
-// ticks earlier, from {value, epoch} words requested from global memory kF ticks before
-// that, so in steady state nobody polls: every warp only waits in the hardware barrier.
-//
-// Critical path of a tick: barrier release -> LDS of the k-neighbour -> DMUL, 3 x DADD
-// (the reference's operation order) -> STS -> barrier arrive.  Everything else (operand
-// loads kD steps ahead into a rotating register FIFO, the j/i terms, stores to global
-// memory, publication for other CTAs) is issued after the arrive, in the barrier's shadow.
+// One stack of up to W planes of one column.  The planes tick together through named barrier 1:
+// in interval T plane p executes its step n = T - p, reading what plane p-1 wrote in interval
+// T-1 (measured on B200, tests/micro/sync_latency.cu: bar.sync + LDS + 4 dependent FP64 ops +
+// STS = 105 cycles per tick for 8 warps; an mbarrier costs 150-370).  Every step of every plane
+// costs the same (a straggler delays all planes every tick): the operand rows of the next kD
+// steps stream through a cp.async ring, one commit group per step, so no step has a refill
+// burst and nothing waits on register scoreboards shared with younger loads.
+// The helper warp is not part of the barrier.  It polls the {value, epoch} words other CTAs
+// publish in global memory (the plane below the stack, the last line of the previous column),
+// four rows per round trip, and forwards them into tagged rings in shared memory, as far
+// ahead as the ring allows; only the first plane and the edge lanes ever look at a tag.
 template <int W, bool BWD>
 __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
 {
@@ -231,9 +207,12 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
         sh->abort = 0;
         sh->finished = 0;
     }
+    if (threadIdx.x < 32) sh->prog[threadIdx.x] = 0;
     {
-        double* q0 = &sm->hk[0][0];   // zero rows: what a plane without a k-neighbour reads
-        for (int q = threadIdx.x; q < kRing * 32 + W * kRing; q += (W + 1) * 32) q0[q] = 0.0;
+        // tags 0 everywhere: never equal to n + 1
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        uint4* q0 = reinterpret_cast<uint4*>(&sm->hk[0][0]);
+        for (int q = threadIdx.x; q < kRing * 32 + W * kRing; q += (W + 1) * 32) q0[q] = z;
     }
     __syncthreads();
 
@@ -250,11 +229,7 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
     const unsigned int epoch = a.epoch;
     const long long tileStride = (long long)steps * 32;
     const int t0 = BWD ? steps - 1 : 0, dt = BWD ? -1 : 1;
-    // The planes of a stack and the helper tick together through named barrier 1 (measured on
-    // B200, tests/micro/sync_latency.cu: bar.sync + LDS + 4 dependent FP64 ops + STS = 105
-    // cycles per tick for 8 warps, 142 for 16; an mbarrier costs 150-370).  Everything of a
-    // step that does not feed the hand-off is issued after the barrier instruction.
-    const int nThreads = (Wg + 1) * 32;
+    const int nThreads = Wg * 32;
     auto tick = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nThreads) : "memory"); };
     unsigned long long* trace = a.trace ? a.trace + 8ull * (unsigned int)sh->ticket : nullptr;
     if (trace && threadIdx.x == 0) {
@@ -273,6 +248,7 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
             const bool hasJ = lineValid && (BWD ? (j < ny - 1) : (j > 0));
             const bool edgeIn = jIn && hasJ && (BWD ? (lane == 31) : (lane == 0));
             const bool edgeOut = lineValid && jOut && (BWD ? (lane == 0) : (lane == 31));
+            const bool fromHelper = (p == 0) && prevGroup;       // warp-uniform
             const bool hasConsumer = p + 1 < Wg;
             const bool pubK = (p == Wg - 1) && nextGroup;
             const long long base = (long long)T * tileStride + lane;
@@ -280,122 +256,122 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
             const double* pPj = a.pj + base;
             const double* pPi = a.pi + base;
             double* pY = a.Y + base;
-            // k-neighbour values: the plane below in this stack (2 slots) or the helper's ring
-            const unsigned int kIn = (unsigned int)__cvta_generic_to_shared(p > 0 ? &sm->kx[p - 1][0][lane] : &sm->hk[0][lane]);
-            const unsigned int kMask = p > 0 ? 1u : (unsigned int)(kRing - 1);
+            const unsigned int kIn = (unsigned int)__cvta_generic_to_shared(&sm->kx[p > 0 ? p - 1 : 0][0][lane]);
             const unsigned int kOut = (unsigned int)__cvta_generic_to_shared(&sm->kx[p][0][lane]);
-            const unsigned int jInA = (unsigned int)__cvta_generic_to_shared(&sm->hj[p][0]);
+            const unsigned int hkA = (unsigned int)__cvta_generic_to_shared(&sm->hk[0][lane]);
+            const unsigned int hjA = (unsigned int)__cvta_generic_to_shared(&sm->hj[p][0]);
+            const unsigned int opsA = (unsigned int)__cvta_generic_to_shared(&sm->ops[p][0][0][lane]);
             LLW* gKself = a.gK + ((long long)(kg * nJ + J) * steps) * 32 + lane;
             LLW* gJself = a.gJ + (long long)T * steps;
             const unsigned int nxEff = lineValid ? (unsigned int)nx : 0u;   // cell i = t - lane exists iff i < nxEff
             const int iFirst = BWD ? nx - 1 : 0;                            // cell without an i-neighbour
 
-            // Operand stream: TMA.  The rows of a chunk of kC steps are contiguous in the tile layout
-            // (kC * 256 bytes per operand), so one lane fetches them with four cp.async.bulk copies
-            // into a ring of kNS chunks in shared memory, completion on an mbarrier per ring slot.
-            // (Register-destined loads all hang on the warp's few counting scoreboards - waiting for
-            // the oldest row waits for the youngest too; per-lane cp.async costs the LSU 8 cycles per
-            // instruction and warp, measured as 35 cycles per warp and tick.)
-            const unsigned int opsA = (unsigned int)__cvta_generic_to_shared(&sm->ops[p][0][0][0][0]);
-            const unsigned int fullA = (unsigned int)__cvta_generic_to_shared(&sm->full[p][0]);
-            if (lane == 0)
-                for (int q = 0; q < kNS; q++) mbar_init(fullA + 8u * q, 1);
-            __syncwarp();
-            const int nChunks = (steps + kC - 1) / kC;
-            auto issue = [&](int c, unsigned int slot) {   // lane 0: rows of steps kC*c .. kC*c + kC-1
-                const int n0 = c * kC;
-                const int rowLo = BWD ? t0 - n0 - (kC - 1) : n0;      // lowest row of the chunk
-                const long long e = (long long)rowLo * 32 - lane;      // p* pointers carry + lane
-                const unsigned int d = opsA + slot * (4u * kC * 256u);
-                const unsigned int bar = fullA + 8u * slot;
-                mbar_expect_tx(bar, 4u * kC * 256u);
-                bulk_g2s(d, pPk + e, kC * 256u, bar);
-                bulk_g2s(d + kC * 256u, pPj + e, kC * 256u, bar);
-                bulk_g2s(d + 2u * kC * 256u, pPi + e, kC * 256u, bar);
-                bulk_g2s(d + 3u * kC * 256u, pY + e, kC * 256u, bar);
+            auto issue = [&](int n_, unsigned int slot) {
+                const long long e = (long long)(t0 + dt * n_) * 32;
+                const unsigned int d = opsA + slot * 1024u;
+                cp_async8(d, pPk + e);
+                cp_async8(d + 256u, pPj + e);
+                cp_async8(d + 512u, pPi + e);
+                cp_async8(d + 768u, pY + e);
+                cp_async_commit();
             };
-            auto fetch = [&](unsigned int slot, int q, StepOps2& o) {   // step q of the chunk in `slot`
-                const unsigned int r = (unsigned int)(BWD ? kC - 1 - q : q);
-                const unsigned int d = opsA + slot * (4u * kC * 256u) + r * 256u + (unsigned int)lane * 8u;
+            auto fetch = [&](unsigned int slot, StepOps2& o) {
+                const unsigned int d = opsA + slot * 1024u;
                 o.pk = lds64(d);
-                o.pj = lds64(d + kC * 256u);
-                o.pi = lds64(d + 2u * kC * 256u);
-                o.src = lds64(d + 3u * kC * 256u);
+                o.pj = lds64(d + 256u);
+                o.pi = lds64(d + 512u);
+                o.src = lds64(d + 768u);
             };
-            if (lane == 0)
-                for (int c = 0; c < kNS && c < nChunks; c++) issue(c, (unsigned int)c);
-            for (int q = 0; q <= p; q++) tick();   // plane p starts in interval p
+            bool dead = false;
+            // value of a word the helper forwards; polls shared memory while it is not there yet
+            auto helper_word = [&](unsigned int addr, unsigned int tag, bool need) -> double {
+                LLW w;
+                s_peek_a(addr, w);
+                if (__any_sync(0xffffffffu, need && !ok(w, tag))) {
+                    long long tstart = 0;
+                    for (int spin = 0; !dead; spin++) {
+                        s_peek_a(addr, w);
+                        if (!__any_sync(0xffffffffu, need && !ok(w, tag))) break;
+                        if ((spin & 1023) == 1023 && give_up(sh, tstart)) dead = true;
+                    }
+                }
+                return val(w);
+            };
+#pragma unroll
+            for (int q = 0; q < kD; q++) issue(q, (unsigned int)q);
+            for (int q = 0; q < p; q++) tick();   // plane p starts in interval p
 
             StepOps2 o;   // operands of the coming step
-            mbar_wait(fullA, 0u);
-            fetch(0u, 0, o);
+            cp_async_wait<kD - 1>();
+            fetch(0u, o);
             double prev = 0.0;
-            // j- and i-terms of the coming step: known before the barrier opens.  Step 0 only has
-            // the edge lane's cell (i == iFirst): no i-term, a j-term if a column feeds this one.
+            // k-neighbour value and j- / i-terms of the coming step.  Step 0 only has the edge
+            // lane's cell (i == iFirst): no i-term, a j-term if a column feeds this one.
+            double vk = 0.0;   // no k-neighbour: pk == +0 too and src stays as it is
+            if (p > 0) vk = lds64(kIn);
+            else if (fromHelper) vk = helper_word(hkA, 1u, true);
             double ti = 0.0;
-            double tj = edgeIn ? __dmul_rn(o.pj, lds64(jInA)) : 0.0;
-            unsigned int slot = 0, useCount = 0;   // ring slot of the current chunk, times the ring wrapped
-            for (int c = 0; c < nChunks; c++) {
-                const int tb = t0 + dt * c * kC;
-                const unsigned int nextSlot = slot + 1 == kNS ? 0u : slot + 1;
-                const unsigned int nextUse = slot + 1 == kNS ? useCount + 1 : useCount;
+            double tj = 0.0;
+            if (jIn) {
+                const double vje = helper_word(hjA, 1u, edgeIn);
+                if (edgeIn) tj = __dmul_rn(o.pj, vje);
+            }
+            for (int nb = 0; nb < steps; nb += kD) {
+                const int tb = t0 + dt * nb;
 #pragma unroll
-                for (int q = 0; q < kC; q++) {
-                    const unsigned int n = (unsigned int)(c * kC + q);
+                for (int q = 0; q < kD; q++) {
+                    const unsigned int n = (unsigned int)(nb + q);
                     if ((int)n < steps) {
                         const int t = tb + dt * q;
                         const int i = t - lane;
                         const bool active = (unsigned int)i < nxEff;
-                        // ---- critical path: k-neighbour -> result -> hand-off -> barrier
-                        const double vk = lds64(kIn + (n & kMask) * 256u);
-                        // without a k-neighbour pk == +0 and vk == +0: src stays as it is
+                        // ---- result -> hand-off -> barrier
                         double acc = __dsub_rn(o.src, __dmul_rn(o.pk, vk));
                         acc = __dsub_rn(acc, tj);    // tj, ti == +0 where the neighbour does not exist
                         acc = __dsub_rn(acc, ti);
                         if (hasConsumer) sts64(kOut + (n & 1u) * 256u, acc);
-                        if (trace && lane == 0 && sh->ticket == a.prefetch && n + p + 1 >= 110u && n + p + 1 < 138u)
-                            a.trace[8ull * nCta + (unsigned long long)p * 28ull + (n + p + 1 - 110u)] = (unsigned long long)clock64();
                         tick();
-                        // ---- behind the barrier instruction: nothing here feeds another warp this tick
-                        if (active) {
-                            pY[t * 32] = acc;
-                            prev = acc;
-                        }
-                        if (pubK) g_store(gKself + t * 32, acc, epoch);
-                        if (edgeOut && active) g_store(gJself + t, acc, epoch);
-                        if (q + 1 < kC) {
-                            fetch(slot, q + 1, o);
-                        } else {
-                            // every lane has its operands of this chunk in registers: refill the slot,
-                            // then move on to the next chunk (its bytes landed long ago)
-                            __syncwarp();
-                            if (lane == 0 && c + kNS < nChunks) issue(c + kNS, slot);
-                            if (c + 1 < nChunks) {
-                                mbar_wait(fullA + 8u * nextSlot, nextUse & 1u);
-                                fetch(nextSlot, 0, o);
-                            }
-                        }
+                        // ---- first what the next result waits for longest: the k-neighbour's value
+                        if (p > 0) vk = lds64(kIn + ((n + 1u) & 1u) * 256u);
+                        else if (fromHelper) vk = helper_word(hkA + ((n + 1u) & (unsigned int)(kRing - 1)) * 512u, n + 2u, (int)n + 1 < steps);
+                        fetch((unsigned int)((q + 1) % kD), o);        // landed: see the wait below
+                        if (active) prev = acc;
                         {   // terms of step n + 1
                             double vj = BWD ? __shfl_down_sync(0xffffffffu, prev, 1) : __shfl_up_sync(0xffffffffu, prev, 1);
-                            const double vje = lds64(jInA + ((n + 1u) & (unsigned int)(kRing - 1)) * 8u);
-                            if (edgeIn) vj = vje;
+                            if (jIn) {
+                                const bool need = edgeIn && (unsigned int)(i + dt) < nxEff;
+                                const double vje = helper_word(hjA + ((n + 1u) & (unsigned int)(kRing - 1)) * 16u, n + 2u, need);
+                                if (edgeIn) vj = vje;
+                            }
                             tj = hasJ ? __dmul_rn(o.pj, vj) : 0.0;
                             ti = (i + dt != iFirst) ? __dmul_rn(o.pi, prev) : 0.0;
                         }
+                        // ---- then what nobody in this CTA waits for
+                        if (active) pY[t * 32] = acc;
+                        if (pubK) g_store(gKself + t * 32, acc, epoch);     // warp-uniform branch
+                        if (jOut) {
+                            if (edgeOut && active) g_store(gJself + t, acc, epoch);
+                        }
+                        issue((int)n + kD, (unsigned int)q);          // this step's slot is free again
+                        cp_async_wait<kD - 2>();                       // the rows of step n + 2 have landed
+                        if (((q + 1) & 3) == 0 && lane == 0) sh->prog[p] = (int)n + 1;
                     }
                 }
-                slot = nextSlot;
-                useCount = nextUse;
             }
+            cp_async_wait<0>();
             for (int q = p + 1; q < Wg; q++) tick();
+            if (dead) {
+                sh->abort = 1;
+                a.S->commError = 2;
+                a.S->done = 1;
+            }
+            __syncwarp();
+            if (lane == 0) sh->prog[p] = steps;
             if (trace && lane == 0 && p == 0) trace[2] = gtimer();
             if (trace && lane == 0 && p == Wg - 1) trace[3] = gtimer();
         }
     } else {
         // ------------------------------------------------------------------ helper warp
-        // k-row r (needed by plane 0 in interval r) and j-row r of plane q (needed in interval
-        // r + q) enter shared memory kA ticks early; their global words are requested kF
-        // ticks before that.  A word that is not there yet when its turn comes is polled.
         const int kgProd = BWD ? kg + 1 : kg - 1;
         const LLW* gKrow = a.gK + ((long long)((prevGroup ? kgProd : kg) * nJ + J) * steps) * 32 + lane;
         const int kq = BWD ? k0 + Wg - 1 - lane : k0 + lane;           // plane of stack position `lane`
@@ -406,78 +382,53 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
         const int nkEnd = prevGroup ? steps : 0;
         const int njEnd = (jIn && lane < Wg) ? nx : 0;
         const int jShift = BWD ? -31 : 31;
-        const long long pbase = (long long)Tq * tileStride;
-        const bool pfK = (lane > 0) || prevGroup;
-        bool dead = false;
+        int nk = 0, nj = 0;     // rows forwarded so far (nj: for the plane of this lane)
+        long long tstart = 0;
         unsigned long long loops = 0;
-        LLW wk[kF], wj[kF];
+        for (int spin = 0;; loops++) {
+            const int pr = (lane < Wg) ? sh->prog[lane] : 0x7fffffff;
+            const int minProg = __reduce_min_sync(0xffffffffu, pr);
+            const int p0 = __shfl_sync(0xffffffffu, pr, 0);
+            if (__any_sync(0xffffffffu, sh->abort != 0)) break;
+            bool did = false;
+            // a ring slot is free again once its reader has finished the step kRing before;
+            // prog is published every 4 steps
+            const int capK = min(nkEnd, p0 + kRing - 1), capJ = min(njEnd, pr + kRing - 1);
+            LLW wk[4], wj[4];
 #pragma unroll
-        for (int q = 0; q < kF; q++) wk[q].f0 = wk[q].f1 = wj[q].f0 = wj[q].f1 = 0u;
-
-        // forward k-row rk and this lane's j-row rj (if they exist) from the words in hand,
-        // polling global memory for any that has not been published yet
-        auto forward = [&](int rk, int rj, LLW& k_, LLW& j_) {
-            const bool doK = rk >= 0 && rk < nkEnd;          // warp-uniform
-            const bool doJ = rj >= 0 && rj < njEnd;          // per lane
-            long long tstart = 0;
-            for (int spin = 0; !dead; spin++) {
-                const bool bad = (doK && !ok(k_, epoch)) || (doJ && !ok(j_, epoch));
-                if (!__any_sync(0xffffffffu, bad)) break;
-                loops++;
-                if (doK) g_peek(gKrow + (t0 + dt * rk) * 32, k_);
-                if (doJ) g_peek(gJrow + (t0 + dt * rj + jShift), j_);
-                if ((spin & 63) == 63 && give_up(sh, tstart)) dead = true;
+            for (int q = 0; q < 4; q++) {
+                if (nk + q < capK) g_peek(gKrow + (t0 + dt * (nk + q)) * 32, wk[q]);
+                if (nj + q < capJ) g_peek(gJrow + (t0 + dt * (nj + q) + jShift), wj[q]);
             }
-            if (doK) sts64(hkA + (unsigned int)(rk & (kRing - 1)) * 256u, val(k_));
-            if (doJ) sts64(hjA + (unsigned int)(rj & (kRing - 1)) * 8u, val(j_));
-        };
-        auto request = [&](int rk, int rj, LLW& k_, LLW& j_) {
-            if (rk >= 0 && rk < nkEnd) g_peek(gKrow + (t0 + dt * rk) * 32, k_);
-            if (rj >= 0 && rj < njEnd) g_peek(gJrow + (t0 + dt * rj + jShift), j_);
-        };
-
-        // rows of the first kA intervals, then the requests of the next kF
-        for (int r = 0; r < kA; r++) {
-            LLW k_, j_;
-            k_.f0 = k_.f1 = j_.f0 = j_.f1 = 0u;
-            forward(r, r - lane, k_, j_);
-        }
 #pragma unroll
-        for (int q = 0; q < kF; q++) request(kA + q, kA + q - lane, wk[q], wj[q]);
-
-        const int total = steps + Wg;
-        for (int Tb = 0; Tb < total; Tb += kF) {
+            for (int q = 0; q < 4; q++) {   // k-rows: all lanes of a row must be there
+                if (nk >= capK || !__all_sync(0xffffffffu, ok(wk[q], epoch))) break;
+                s_store_a(hkA + (unsigned int)(nk & (kRing - 1)) * 512u, wk[q].lo, wk[q].hi, (unsigned int)nk + 1u);
+                nk++;
+                did = true;
+            }
 #pragma unroll
-            for (int q = 0; q < kF; q++) {
-                const int T = Tb + q;
-                if (T < total) {
-                    // interval T-1 is running and reads rows T-1 (k) and T-1-lane (j)
-                    forward(T + kA, T + kA - lane, wk[q], wj[q]);
-                    request(T + kA + kF, T + kA + kF - lane, wk[q], wj[q]);
-                    if (false && lane < Wg && ((T - lane) & (kPfChunk - 1)) == 0) {
-                        // operand rows kPfAhead steps ahead of plane `lane` into L2
-                        const int r0 = T - lane + kPfAhead;
-                        const int nrows = min(kPfChunk, steps - r0);
-                        if (r0 >= 0 && nrows > 0) {
-                            const int tlo = BWD ? steps - r0 - nrows : r0;
-                            const long long off = pbase + (long long)tlo * 32;
-                            const unsigned int bytes = (unsigned int)nrows * 256u;
-                            if (pfK) l2_prefetch(a.pk + off, bytes);
-                            l2_prefetch(a.pj + off, bytes);
-                            l2_prefetch(a.pi + off, bytes);
-                            l2_prefetch(a.Y + off, bytes);
-                        }
-                    }
-                    if (trace && lane == 0 && sh->ticket == a.prefetch && T >= 110 && T < 138)
-                        a.trace[8ull * nCta + (unsigned long long)W * 28ull + (T - 110)] = (unsigned long long)clock64();
-                    tick();
+            for (int q = 0; q < 4; q++) {   // j-words: every lane for its own plane
+                if (nj >= capJ || !ok(wj[q], epoch)) break;
+                s_store_a(hjA + (unsigned int)(nj & (kRing - 1)) * 16u, wj[q].lo, wj[q].hi, (unsigned int)nj + 1u);
+                nj++;
+                did = true;
+            }
+            did = __any_sync(0xffffffffu, did);
+            const bool jDone = __all_sync(0xffffffffu, nj >= njEnd);
+            if (nk >= nkEnd && jDone) break;    // everything forwarded: the planes finish alone
+            if (did) {
+                spin = 0;
+                tstart = 0;
+            } else {
+                spin++;
+                if ((spin & 63) == 63 && give_up(sh, tstart)) {
+                    sh->abort = 1;
+                    a.S->commError = 2;
+                    a.S->done = 1;
+                    break;
                 }
             }
-        }
-        if (dead) {
-            sh->abort = 1;
-            a.S->commError = 2;
-            a.S->done = 1;
         }
         if (trace && lane == 0) {
             trace[4] = loops;
@@ -629,8 +580,8 @@ void free_padded2(void* user, size_t elemBytes)
 
 size_t smem_bytes(int W)
 {
-    return ((size_t)W * 2 * 32 + (size_t)kRing * 32 + (size_t)W * kRing + (size_t)W * kNS * 4 * kC * 32 + (size_t)W * kNS) * sizeof(double)
-           + sizeof(Shared2) + 64;
+    return (size_t)W * 2 * 32 * sizeof(double) + ((size_t)kRing * 32 + (size_t)W * kRing) * sizeof(LLW)
+           + (size_t)W * kD * 4 * 32 * sizeof(double) + sizeof(Shared2) + 64;
 }
 
 int pick_W(int nz)
@@ -638,9 +589,9 @@ int pick_W(int nz)
     const char* e = getenv("LDU_STENCIL_W");
     if (e) {
         const int w = atoi(e);
-        if (w == 4 || w == 8 || w == 15 || w == 16) return w;
+        if (w == 2 || w == 3 || w == 4 || w == 6 || w == 8 || w == 15 || w == 16) return w;
     }
-    return nz >= 32 ? 15 : (nz >= 6 ? 8 : 4);
+    return nz >= 12 ? 6 : 4;
 }
 
 int state2(ldu_matrix* m, State2** out)
@@ -725,15 +676,15 @@ int launch_sweeps(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
     a.pi = P.F[2];
     const char* tracePath = getenv("LDU_S2_TRACE");
     if (tracePath && !s->trace) {
-        LDU_CUDA(cudaMalloc((void**)&s->trace, ((size_t)grid * 8 + 17 * 28) * sizeof(unsigned long long)));
+        LDU_CUDA(cudaMalloc((void**)&s->trace, ((size_t)grid * 8) * sizeof(unsigned long long)));
     }
     a.trace = tracePath ? s->trace : nullptr;
-    if (a.trace) LDU_CUDA(cudaMemsetAsync(a.trace, 0, ((size_t)grid * 8 + 17 * 28) * sizeof(unsigned long long), st));
+    if (a.trace) LDU_CUDA(cudaMemsetAsync(a.trace, 0, ((size_t)grid * 8) * sizeof(unsigned long long), st));
     sweep2_kernel<W, false><<<grid, (W + 1) * 32, smem, st>>>(a);
     count_launch();
     LDU_CUDA(cudaGetLastError());
     if (a.trace) {   // debug only: dump the forward sweep's per-CTA timeline
-        std::vector<unsigned long long> h((size_t)grid * 8 + 17 * 28);
+        std::vector<unsigned long long> h((size_t)grid * 8);
         LDU_CUDA(cudaMemcpyAsync(h.data(), a.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         LDU_CUDA(cudaStreamSynchronize(st));
         if (FILE* f = fopen(tracePath, "w")) {
@@ -741,11 +692,6 @@ int launch_sweeps(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
                 fprintf(f, "%d %d %d %llu %llu %llu %llu %llu %llu %llu %llu\n", c, (int)(h[8 * c] >> 32),
                         (int)(h[8 * c] & 0xffffffffu), h[8 * c + 1], h[8 * c + 2], h[8 * c + 3], h[8 * c + 4], h[8 * c + 5],
                         h[8 * c + 6] & ((1ull << 40) - 1), h[8 * c + 6] >> 40, h[8 * c + 7]);
-            for (int c = 0; c < 17; c++) {
-                fprintf(f, "T%d", c);
-                for (int n = 0; n < 28; n++) fprintf(f, " %llu", h[(size_t)grid * 8 + 28 * c + n]);
-                fprintf(f, "\n");
-            }
             fclose(f);
         }
         a.trace = nullptr;
@@ -814,10 +760,12 @@ int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const d
     a.gK = s->gK;
     a.gJ = s->gJ;
     a.ticket = s->ticket;
-    { const char* e = getenv("LDU_S2_PREFETCH"); a.prefetch = e ? atoi(e) : 0; }
     if (s->W == 16) LDU_TRY(launch_sweeps<16>(m, s, a, P));
     else if (s->W == 15) LDU_TRY(launch_sweeps<15>(m, s, a, P));
     else if (s->W == 8) LDU_TRY(launch_sweeps<8>(m, s, a, P));
+    else if (s->W == 6) LDU_TRY(launch_sweeps<6>(m, s, a, P));
+    else if (s->W == 3) LDU_TRY(launch_sweeps<3>(m, s, a, P));
+    else if (s->W == 2) LDU_TRY(launch_sweeps<2>(m, s, a, P));
     else LDU_TRY(launch_sweeps<4>(m, s, a, P));
     unpack2_kernel<<<gridT, 256, 0, st>>>(s->b, nBlk, s->Y, w, m->d_scalars);
     count_launch();
