@@ -24,10 +24,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 }
 
 template <class T>
-static int upload(ldu_context* ctx, T** d, const T* h, size_t n)
+static int upload(ldu_context* ctx, T** d, const T* h, size_t n, size_t pad = 0)
 {
+    // pad: zeroed elements behind the array (the TMA-staged row kernel copies 16-byte aligned
+    // ranges that may reach a few elements past the end)
     *d = nullptr;
-    LDU_CUDA(cudaMalloc((void**)d, std::max<size_t>(n, 1) * sizeof(T)));
+    LDU_CUDA(cudaMalloc((void**)d, std::max<size_t>(n + pad, 1) * sizeof(T)));
+    if (pad) LDU_CUDA(cudaMemsetAsync(*d + n, 0, pad * sizeof(T), ctx->stream));
     if (n) LDU_CUDA(cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     return LDU_OK;
 }
@@ -325,9 +328,9 @@ int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lower
     for (int k = 0; k < nFaces; k++) lowerCol[k] = m->h_l[m->h_losort[k]];
 
     LDU_TRY(upload(ctx, &m->d_l, m->h_l.data(), nFaces));
-    LDU_TRY(upload(ctx, &m->d_u, m->h_u.data(), nFaces));
-    LDU_TRY(upload(ctx, &m->d_ownerStart, m->h_ownerStart.data(), nCells + 1));
-    LDU_TRY(upload(ctx, &m->d_losortStart, m->h_losortStart.data(), nCells + 1));
+    LDU_TRY(upload(ctx, &m->d_u, m->h_u.data(), nFaces, 8));
+    LDU_TRY(upload(ctx, &m->d_ownerStart, m->h_ownerStart.data(), nCells + 1, kRowBlock + 8));
+    LDU_TRY(upload(ctx, &m->d_losortStart, m->h_losortStart.data(), nCells + 1, kRowBlock + 8));
     LDU_TRY(upload(ctx, &m->d_losort, m->h_losort.data(), nFaces));
     LDU_TRY(upload(ctx, &m->d_lowerCol, lowerCol.data(), nFaces));
     {
@@ -339,11 +342,33 @@ int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lower
                 const int f = m->h_losort[k], l = m->h_l[f];
                 packed[k] = (l << 5) | (f - m->h_ownerStart[l]);
             }
-            LDU_TRY(upload(ctx, &m->d_lowerPacked, packed.data(), nFaces));
+            LDU_TRY(upload(ctx, &m->d_lowerPacked, packed.data(), nFaces, 8));
+            // row blocks for the staged kernel
+            const int nb = (nCells + kRowBlock - 1) / kRowBlock;
+            std::vector<int> desc(4 * (size_t)nb);
+            int fcap = 0, kcap = 0;
+            for (int b = 0; b < nb; b++) {
+                const int r0 = b * kRowBlock, r1 = std::min(nCells, r0 + kRowBlock);
+                const int f0a = m->h_ownerStart[r0] & ~3, k0a = m->h_losortStart[r0] & ~3;
+                const int nFa = (m->h_ownerStart[r1] - f0a + 3) & ~3, nKa = (m->h_losortStart[r1] - k0a + 3) & ~3;
+                desc[4 * b] = f0a;
+                desc[4 * b + 1] = nFa;
+                desc[4 * b + 2] = k0a;
+                desc[4 * b + 3] = nKa;
+                fcap = std::max(fcap, nFa);
+                kcap = std::max(kcap, nKa);
+            }
+            int* d = nullptr;
+            LDU_TRY(upload(ctx, &d, desc.data(), desc.size(), 8));
+            m->d_rowBlocks = d;
+            m->nRowBlocks = nb;
+            m->rowFaceCap = fcap;
+            m->rowLowerCap = kcap;
         }
     }
     LDU_CUDA(cudaMalloc((void**)&m->d_diag, std::max(nCells, 1) * sizeof(double)));
-    LDU_CUDA(cudaMalloc((void**)&m->d_upper, std::max(nFaces, 1) * sizeof(double)));
+    LDU_CUDA(cudaMalloc((void**)&m->d_upper, ((size_t)nFaces + 8) * sizeof(double)));
+    LDU_CUDA(cudaMemsetAsync(m->d_upper + nFaces, 0, 8 * sizeof(double), ctx->stream));
     m->d_lower = m->d_upper;
 
     // interfaces, concatenated interface-major
@@ -415,6 +440,7 @@ int ldu_matrix_destroy(ldu_matrix* m)
     cudaFree(m->d_losort);
     cudaFree(m->d_lowerCol);
     cudaFree(m->d_lowerPacked);
+    cudaFree(m->d_rowBlocks);
     cudaFree(m->d_diag);
     cudaFree(m->d_upper);
     if (m->ownLower) cudaFree(m->d_lower);
@@ -441,7 +467,8 @@ int ldu_matrix_destroy(ldu_matrix* m)
 static int set_lower_storage(ldu_matrix* m, bool asym)
 {
     if (asym && !m->ownLower) {
-        LDU_CUDA(cudaMalloc((void**)&m->d_lower, std::max(m->nFaces, 1) * sizeof(double)));
+        LDU_CUDA(cudaMalloc((void**)&m->d_lower, ((size_t)m->nFaces + 8) * sizeof(double)));
+        LDU_CUDA(cudaMemsetAsync(m->d_lower + m->nFaces, 0, 8 * sizeof(double), m->ctx->stream));
         m->ownLower = true;
     } else if (!asym && m->ownLower) {
         LDU_CUDA(cudaStreamSynchronize(m->ctx->stream));

@@ -63,6 +63,7 @@ struct SolverScalars {
     double* hist;       // [kMaxHist] normalised residual after every iteration
 };
 
+constexpr int kRowBlock = 512;     // rows per block of the TMA-staged row kernel (amul.cu)
 constexpr int kMaxRed = 4;         // values reduced together per kernel
 constexpr int kMaxHist = 4096;     // residual history entries kept on device
 
@@ -145,6 +146,10 @@ struct ldu_matrix {
     // column owns, i.e. face = ownerStart[column] + (word & 31).  Null when a cell owns more
     // than 32 faces or nCells >= 2^26 (then losort/lowerCol are used).
     int* d_lowerPacked = nullptr;
+    // row blocks of the TMA-staged row kernel (amul.cu): per block of kRowBlock rows the
+    // 16-byte aligned face / lower-entry ranges {f0a, nFa, k0a, nKa}; capacities of a stage
+    void* d_rowBlocks = nullptr;
+    int nRowBlocks = 0, rowFaceCap = 0, rowLowerCap = 0;
     // host copies (schedules, agglomeration)
     std::vector<int> h_l, h_u, h_ownerStart, h_losortStart, h_losort;
     // coefficients (device)

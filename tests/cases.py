@@ -15,6 +15,10 @@ SYSTEMS = {
     # several stacks of k-planes and two columns (plane-stacked sweeps, stencil2.cu)
     "box6x40x9": dict(nx=6, ny=40, nz=9, variable=True),
     "asym4x35x13": dict(nx=4, ny=35, nz=13, variable=True, asym=0.2),
+    # more than 8 row blocks of 512 rows: the TMA-staged Amul / residual / sumA kernel
+    "box40x30x20": dict(nx=40, ny=30, nz=20, variable=True),
+    "asym33x17x11": dict(nx=33, ny=17, nz=11, variable=True, asym=0.2),
+    "scrambled17": dict(nx=17, ny=17, nz=17, variable=True, scramble=7),
     # randomly renumbered cells: no box structure, generic dataflow sweeps
     "scrambled9": dict(nx=9, ny=9, nz=9, variable=True, scramble=3),
     "scrambled_asym8": dict(nx=8, ny=8, nz=8, variable=True, asym=0.3, scramble=5),
