@@ -281,7 +281,7 @@ def run_ours(args):
                    "precond": args.precond, "iters_per_step": args.iters,
                    "l2": "inputs larger than L2 (0.72 GB per Amul), no flush",
                    "pcg_alg_bytes_per_cell_iter": 352 if args.precond == "DIC" else 208},
-        "roofline": {"bound": "hbm", "kernel": "row_kernel<0> (Amul)", "achieved": amul_gbs, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "row_kernel<0,1,8> (Amul)", "achieved": amul_gbs, "peak": peak,
                      "unit": "GB/s", "frac": amul_gbs / peak, "traffic": None, "peak_source": peak_src,
                      "amul_ms": ms_amul, "alg_bytes_per_launch": amul_bytes},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -290,7 +290,7 @@ def run_ours(args):
         "clocks": clocks,
     }
     traffic_file = ROOT / "profiles" / "amul_dram_bytes.json"
-    if traffic_file.exists():
+    if traffic_file.exists() and world == 1 and n == 216:   # captured on the 216^3 single-region launch
         try:
             line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
         except Exception:

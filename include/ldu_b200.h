@@ -178,6 +178,14 @@ int ldu_tmul(ldu_matrix* m, double* Tpsi, const double* psi);
 int ldu_sumA(ldu_matrix* m, double* sumA);
 /* lduMatrix::residual  lduMatrixATmul.C:203-281 */
 int ldu_residual(ldu_matrix* m, double* rA, const double* psi, const double* source);
+/* lduMatrix::H  matrices/lduMatrix/lduMatrix/lduMatrixTemplates.C:33-65: Hpsi = -(A - diag) psi over the
+ * internal faces (what fvMatrix::H / HbyA = rAU*UEqn.H() of the PISO/SIMPLE step call, icoFoam.C:69-72) */
+int ldu_H(ldu_matrix* m, double* Hpsi, const double* psi);
+/* lduMatrix::H1  lduMatrixATmul.C:298-327: H1 = -rowsum(A - diag) */
+int ldu_H1(ldu_matrix* m, double* H1);
+/* lduMatrix::faceH  lduMatrixTemplates.C:79-113: faceHpsi[nFaces] = upper*psi[u] - lower*psi[l]
+ * (fvMatrix::flux); LDU_EINVAL for a matrix without off-diagonal coefficients (the reference aborts) */
+int ldu_faceH(ldu_matrix* m, double* faceHpsi, const double* psi);
 /* lduMatrix::preconditioner::precondition / preconditionT  lduMatrix.H:482-505 */
 int ldu_precondition(ldu_matrix* m, int preconditioner, double* wA, const double* rA, int transpose);
 /* lduMatrix::smoother::smooth  lduMatrix.H:391-397 (psi in/out) */
@@ -189,6 +197,7 @@ int ldu_solve(ldu_matrix* m, const ldu_controls* controls, double* psi,
 /* ---- operators: fields resident in HBM (ldu_device_alloc'd pointers) ------- */
 int ldu_amul_device(ldu_matrix* m, double* d_Apsi, const double* d_psi);
 int ldu_tmul_device(ldu_matrix* m, double* d_Tpsi, const double* d_psi);
+int ldu_H_device(ldu_matrix* m, double* d_Hpsi, const double* d_psi);
 int ldu_solve_device(ldu_matrix* m, const ldu_controls* controls, double* d_psi,
                      const double* d_source, ldu_solver_performance* perf);
 /* normalised residual after every iteration of the LAST solve on this matrix

@@ -50,6 +50,7 @@ static RowView row_view(const ldu_matrix* m, bool transpose)
 }
 
 // MODE 0: y = A x   1: y = b - A x (residual)   2: y = rowsum(A) (sumA)   3: y = (A - diag) x
+//      4: y = H(x) = -(A - diag) x (lduMatrixTemplates.C:33-65)   5: y = H1 = -rowsum(A - diag) (lduMatrixATmul.C:298-327)
 // One term of a row in the reference's order; `valid` predicates it (rows are processed in
 // batches of kBatch entries whose loads are all issued before the first use, so that a thread
 // has ~2*kBatch gathers in flight instead of one dependent chain per face).
@@ -58,7 +59,8 @@ __device__ __forceinline__ double row_term(double acc, double a, double xv, bool
 {
     double r;
     if (MODE == 0 || MODE == 3) r = __dadd_rn(acc, __dmul_rn(a, xv));
-    else if (MODE == 1) r = __dsub_rn(acc, __dmul_rn(a, xv));
+    else if (MODE == 1 || MODE == 4) r = __dsub_rn(acc, __dmul_rn(a, xv));
+    else if (MODE == 5) r = __dsub_rn(acc, a);
     else r = __dadd_rn(acc, a);
     return valid ? r : acc;
 }
@@ -76,6 +78,7 @@ __device__ __forceinline__ double row_apply(const RowView& v, int c, const doubl
     else if (MODE == 1) acc = __dsub_rn(b[c], __dmul_rn(v.diag[c], x[c]));
     else if (MODE == 2) acc = v.diag[c];
     else acc = 0.0;
+    constexpr bool kNoX = (MODE == 2 || MODE == 5);
     for (int k = k0; k < k1; k += kBatch) {
         int col[kBatch], face[kBatch];
         double a[kBatch], xv[kBatch];
@@ -94,7 +97,7 @@ __device__ __forceinline__ double row_apply(const RowView& v, int c, const doubl
 #pragma unroll
         for (int j = 0; j < kBatch; j++) {
             if (PACKED) face[j] += v.ownerStart[col[j]];
-            if (MODE != 2) xv[j] = x[col[j]];
+            if (!kNoX) xv[j] = x[col[j]];
             else xv[j] = 0.0;
         }
 #pragma unroll
@@ -112,7 +115,7 @@ __device__ __forceinline__ double row_apply(const RowView& v, int c, const doubl
             col[j] = v.u[ff];
         }
 #pragma unroll
-        for (int j = 0; j < kBatch; j++) xv[j] = (MODE != 2) ? x[col[j]] : 0.0;
+        for (int j = 0; j < kBatch; j++) xv[j] = (!kNoX) ? x[col[j]] : 0.0;
 #pragma unroll
         for (int j = 0; j < kBatch; j++) acc = row_term<MODE>(acc, a[j], xv[j], f + j < f1);
     }
@@ -239,8 +242,8 @@ __global__ void __launch_bounds__(kStagedThreads) row_staged_kernel(int n, Stage
             const int c = r0 + tid + q * kStagedThreads;
             dg[q] = xc[q] = bc[q] = 0.0;
             if (c < n) {
-                if (MODE != 3) dg[q] = v.diag[c];
-                if (MODE != 2) xc[q] = x[c];
+                if (MODE <= 2) dg[q] = v.diag[c];
+                if (MODE != 2 && MODE != 5) xc[q] = x[c];
                 if (MODE == 1) bc[q] = b[c];
             }
         }
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kStagedThreads) row_staged_kernel(int n, Stage
 #pragma unroll
                     for (int j = 0; j < kBatch; j++) {
                         face[j] += __ldg(v.ownerStart + col[j]);
-                        xv[j] = (MODE != 2) ? __ldg(x + col[j]) : 0.0;
+                        xv[j] = (MODE != 2 && MODE != 5) ? __ldg(x + col[j]) : 0.0;
                     }
 #pragma unroll
                     for (int j = 0; j < kBatch; j++) a[j] = __ldg(v.lowerCoef + face[j]);
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(kStagedThreads) row_staged_kernel(int n, Stage
                 for (int f = f0; f < f1; f += kBatch) {
                     double xv[kBatch];
 #pragma unroll
-                    for (int j = 0; j < kBatch; j++) xv[j] = (MODE != 2) ? __ldg(x + uS[min(f + j, f1 - 1)]) : 0.0;
+                    for (int j = 0; j < kBatch; j++) xv[j] = (MODE != 2 && MODE != 5) ? __ldg(x + uS[min(f + j, f1 - 1)]) : 0.0;
 #pragma unroll
                     for (int j = 0; j < kBatch; j++)
                         acc = row_term<MODE>(acc, coefS[min(f + j, f1 - 1)], xv[j], f + j < f1);
@@ -340,7 +343,7 @@ static int launch_rows(ldu_matrix* m, const RowView& v, double* y, const double*
     if (m->d_rowBlocks && !stagedOff && !packedOff && n >= 8 * kRowBlock) {
         const unsigned int smem = 2u * staged_stage_bytes(m->rowFaceCap, m->rowLowerCap);
         if (smem <= 200u * 1024u) {
-            static bool attr[4] = {false, false, false, false};
+            static bool attr[6] = {false, false, false, false, false, false};
             if (!attr[MODE]) {
                 LDU_CUDA(cudaFuncSetAttribute(row_staged_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               200 * 1024));
@@ -424,6 +427,37 @@ int k_offdiag(ldu_matrix* m, double* y, const double* x)
     LDU_TRY(comm_halo_put(m, x, false));
     LDU_TRY(launch_rows<3>(m, row_view(m, false), y, x, nullptr, false));
     return k_interfaces_finish(m, y, 0, 1.0, false);
+}
+
+// lduMatrix::H / H1: internal faces only (fvMatrix::H adds the boundary part itself)
+int k_H(ldu_matrix* m, double* Hpsi, const double* psi)
+{
+    return launch_rows<4>(m, row_view(m, false), Hpsi, psi, nullptr, false);
+}
+
+int k_H1(ldu_matrix* m, double* H1)
+{
+    return launch_rows<5>(m, row_view(m, false), H1, nullptr, nullptr, false);
+}
+
+// lduMatrix::faceH (lduMatrixTemplates.C:79-113): upper*psi[u] - lower*psi[l] per face
+__global__ void __launch_bounds__(kBlock) faceH_kernel(int nFaces, const int* __restrict__ l, const int* __restrict__ u,
+                                                        const double* __restrict__ lower,
+                                                        const double* __restrict__ upper,
+                                                        const double* __restrict__ psi, double* __restrict__ out)
+{
+    for (int f = blockIdx.x * kBlock + threadIdx.x; f < nFaces; f += gridDim.x * kBlock)
+        out[f] = __dsub_rn(__dmul_rn(upper[f], psi[u[f]]), __dmul_rn(lower[f], psi[l[f]]));
+}
+
+int k_faceH(ldu_matrix* m, double* faceHpsi, const double* psi)
+{
+    if (m->nFaces <= 0) return LDU_OK;
+    faceH_kernel<<<grid_for(m->ctx, m->nFaces), kBlock, 0, m->ctx->stream>>>(m->nFaces, m->d_l, m->d_u, m->d_lower,
+                                                                            m->d_upper, psi, faceHpsi);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
 }
 
 int k_sumA(ldu_matrix* m, double* sumA)

@@ -235,6 +235,9 @@ int k_amul(ldu_matrix* m, double* Apsi, const double* psi, bool transpose, bool 
 int k_interfaces(ldu_matrix* m, double* result, const double* psi, int whichCoeffs, double sign,
                  bool guarded = false);
 int k_sumA(ldu_matrix* m, double* sumA);
+int k_H(ldu_matrix* m, double* Hpsi, const double* psi);        // lduMatrix::H
+int k_H1(ldu_matrix* m, double* H1);                             // lduMatrix::H1
+int k_faceH(ldu_matrix* m, double* faceHpsi, const double* psi);  // lduMatrix::faceH (face-sized output)
 int k_offdiag(ldu_matrix* m, double* y, const double* x);   // (A - diag) x, GAMGSolverInterpolate.C:50-76
 int k_residual(ldu_matrix* m, double* rA, const double* psi, const double* source, bool guarded = false);
 

@@ -737,6 +737,52 @@ int ldu_residual(ldu_matrix* m, double* rA, const double* psi, const double* sou
     return s.out(rA, dy);
 }
 
+int ldu_H(ldu_matrix* m, double* Hpsi, const double* psi)
+{
+    LDU_TRY(check_matrix(m, "ldu_H"));
+    Staged s{m};
+    double* dx = s.in(W_PSI, psi);
+    double* dy = work_vec(m, W_OUT);
+    LDU_TRY(k_H(m, dy, dx));
+    return s.out(Hpsi, dy);
+}
+
+int ldu_H1(ldu_matrix* m, double* H1)
+{
+    LDU_TRY(check_matrix(m, "ldu_H1"));
+    Staged s{m};
+    double* dy = work_vec(m, W_OUT);
+    LDU_TRY(k_H1(m, dy));
+    return s.out(H1, dy);
+}
+
+int ldu_faceH(ldu_matrix* m, double* faceHpsi, const double* psi)
+{
+    LDU_TRY(check_matrix(m, "ldu_faceH"));
+    if (m->nFaces <= 0) {   // the reference aborts: "the matrix does not have any off-diagonal coefficients"
+        set_error("ldu_faceH: the matrix does not have any off-diagonal coefficients");
+        return LDU_EINVAL;
+    }
+    Staged s{m};
+    double* dx = s.in(W_PSI, psi);
+    double* dy = nullptr;
+    cudaStream_t st = m->ctx->stream;
+    LDU_CUDA(cudaMallocAsync((void**)&dy, (size_t)m->nFaces * sizeof(double), st));
+    int rc = k_faceH(m, dy, dx);
+    if (rc == LDU_OK
+        && cudaMemcpyAsync(faceHpsi, dy, (size_t)m->nFaces * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = LDU_ECUDA;
+    cudaFreeAsync(dy, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = LDU_ECUDA;
+    return rc;
+}
+
+int ldu_H_device(ldu_matrix* m, double* d_Hpsi, const double* d_psi)
+{
+    LDU_TRY(check_matrix(m, "ldu_H_device"));
+    return k_H(m, d_Hpsi, d_psi);
+}
+
 int ldu_precondition(ldu_matrix* m, int preconditioner, double* wA, const double* rA, int transpose)
 {
     LDU_TRY(check_matrix(m, "ldu_precondition"));

@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "ldu_context_synchronize", "ldu_context_stream", "ldu_comm_window_create", "ldu_comm_connect",
     "ldu_device_alloc", "ldu_device_free", "ldu_copy_h2d", "ldu_copy_d2h", "ldu_device_memset", "ldu_host_alloc",
     "ldu_host_free", "ldu_matrix_create", "ldu_matrix_destroy", "ldu_matrix_set_coeffs",
-    "ldu_matrix_set_coeffs_device", "ldu_matrix_set_face_weights", "ldu_amul", "ldu_tmul", "ldu_sumA",
+    "ldu_matrix_set_coeffs_device", "ldu_matrix_set_face_weights", "ldu_amul", "ldu_tmul", "ldu_sumA", "ldu_H", "ldu_H1", "ldu_faceH", "ldu_H_device",
     "ldu_residual", "ldu_precondition", "ldu_smooth", "ldu_solve", "ldu_amul_device", "ldu_tmul_device",
     "ldu_solve_device", "ldu_residual_history", "ldu_gamg_build", "ldu_gamg_nlevels",
     "ldu_gamg_level_sizes", "ldu_gamg_level_restrict", "ldu_gamg_level_coeffs", "ldu_controls_default",
@@ -92,6 +92,10 @@ def library():
         L.ldu_amul.argtypes = [vp, vp, vp]
         L.ldu_tmul.argtypes = [vp, vp, vp]
         L.ldu_sumA.argtypes = [vp, vp]
+        L.ldu_H.argtypes = [vp, vp, vp]
+        L.ldu_H1.argtypes = [vp, vp]
+        L.ldu_faceH.argtypes = [vp, vp, vp]
+        L.ldu_H_device.argtypes = [vp, vp, vp]
         L.ldu_residual.argtypes = [vp, vp, vp, vp]
         L.ldu_precondition.argtypes = [vp, i, vp, vp, i]
         L.ldu_smooth.argtypes = [vp, i, vp, vp, i]
@@ -380,6 +384,26 @@ class lduMatrix:
     def sumA(self) -> np.ndarray:
         out = np.empty(self.nCells)
         _check(self.L.ldu_sumA(self.h, out.ctypes.data), "ldu_sumA")
+        return out
+
+    def H(self, psi) -> np.ndarray:
+        """lduMatrix::H (lduMatrixTemplates.C:33-65)"""
+        psi = _f64(psi)
+        out = np.empty(self.nCells)
+        _check(self.L.ldu_H(self.h, out.ctypes.data, psi.ctypes.data), "ldu_H")
+        return out
+
+    def H1(self) -> np.ndarray:
+        """lduMatrix::H1 (lduMatrixATmul.C:298-327)"""
+        out = np.empty(self.nCells)
+        _check(self.L.ldu_H1(self.h, out.ctypes.data), "ldu_H1")
+        return out
+
+    def faceH(self, psi) -> np.ndarray:
+        """lduMatrix::faceH (lduMatrixTemplates.C:79-113): one value per face"""
+        psi = _f64(psi)
+        out = np.empty(self.nFaces)
+        _check(self.L.ldu_faceH(self.h, out.ctypes.data, psi.ctypes.data), "ldu_faceH")
         return out
 
     def residual(self, psi, source) -> np.ndarray:

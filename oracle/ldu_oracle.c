@@ -70,6 +70,50 @@ struct orc_world {
     int hBuilt;
 };
 
+/* lduMatrix::H: LM/lduMatrix/lduMatrixTemplates.C:33-65 (off-diagonal product, negated;
+ * no interface terms: fvMatrix::H adds the boundary contributions itself) */
+void orc_H(orc_world* w, double** Hpsi, double** psi)
+{
+    int r, c, f;
+    for (r = 0; r < w->R; r++) {
+        const orc_matrix* m = &w->m[r];
+        double* H = Hpsi[r];
+        const double* x = psi[r];
+        for (c = 0; c < m->nCells; c++) H[c] = 0.0;
+        for (f = 0; f < m->nFaces; f++) {
+            H[m->u[f]] -= m->lower[f] * x[m->l[f]];
+            H[m->l[f]] -= m->upper[f] * x[m->u[f]];
+        }
+    }
+}
+
+/* lduMatrix::H1: LM/lduMatrix/lduMatrixATmul.C:298-327 */
+void orc_H1(orc_world* w, double** H1)
+{
+    int r, c, f;
+    for (r = 0; r < w->R; r++) {
+        const orc_matrix* m = &w->m[r];
+        double* H = H1[r];
+        for (c = 0; c < m->nCells; c++) H[c] = 0.0;
+        for (f = 0; f < m->nFaces; f++) {
+            H[m->u[f]] -= m->lower[f];
+            H[m->l[f]] -= m->upper[f];
+        }
+    }
+}
+
+/* lduMatrix::faceH: LM/lduMatrix/lduMatrixTemplates.C:79-113, one value per face */
+void orc_faceH(orc_world* w, double** faceHpsi, double** psi)
+{
+    int r, f;
+    for (r = 0; r < w->R; r++) {
+        const orc_matrix* m = &w->m[r];
+        const double* x = psi[r];
+        for (f = 0; f < m->nFaces; f++)
+            faceHpsi[r][f] = m->upper[f] * x[m->u[f]] - m->lower[f] * x[m->l[f]];
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* addressing                                                                 */
 /* ------------------------------------------------------------------------- */

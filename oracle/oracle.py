@@ -69,9 +69,10 @@ def lib():
         L.orc_world_add_interface.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3
         L.orc_world_add_interface.restype = C.c_int
         L.orc_world_set_face_weights.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        for name in ("orc_amul", "orc_tmul"):
+        for name in ("orc_amul", "orc_tmul", "orc_H", "orc_faceH"):
             getattr(L, name).argtypes = [C.c_void_p, PP, PP]
         L.orc_sumA.argtypes = [C.c_void_p, PP]
+        L.orc_H1.argtypes = [C.c_void_p, PP]
         L.orc_residual.argtypes = [C.c_void_p, PP, PP, PP]
         L.orc_normFactor.argtypes = [C.c_void_p, PP, PP, PP]
         L.orc_normFactor.restype = C.c_double
@@ -158,6 +159,7 @@ class World:
         self._keep = []
         self.w = L.orc_world_new(self.R)
         self.nCells = []
+        self.nFaces = []
         for r, reg in enumerate(regions):
             lo = np.ascontiguousarray(reg["lower"], dtype=np.int32)
             up = np.ascontiguousarray(reg["upper"], dtype=np.int32)
@@ -166,6 +168,7 @@ class World:
             lc = None if reg.get("lowerCoef") is None else _f64(reg["lowerCoef"])
             self._keep += [lo, up, diag, uc, lc]
             self.nCells.append(diag.size)
+            self.nFaces.append(lo.size)
             L.orc_world_set_region(self.w, r, diag.size, lo.size, lo.ctypes.data, up.ctypes.data,
                                    diag.ctypes.data, uc.ctypes.data,
                                    None if lc is None else lc.ctypes.data)
@@ -212,6 +215,26 @@ class World:
     def sumA(self):
         out = self._new()
         self.L.orc_sumA(self.w, _pp(out))
+        return out
+
+    def H(self, psi):
+        """lduMatrix::H (lduMatrixTemplates.C:33-65)"""
+        psi = self._as_list(psi)
+        out = self._new()
+        self.L.orc_H(self.w, _pp(out), _pp(psi))
+        return out
+
+    def H1(self):
+        """lduMatrix::H1 (lduMatrixATmul.C:298-327)"""
+        out = self._new()
+        self.L.orc_H1(self.w, _pp(out))
+        return out
+
+    def faceH(self, psi):
+        """lduMatrix::faceH (lduMatrixTemplates.C:79-113): one value per face"""
+        psi = self._as_list(psi)
+        out = [np.zeros(n) for n in self.nFaces]
+        self.L.orc_faceH(self.w, _pp(out), _pp(psi))
         return out
 
     def residual(self, psi, source):

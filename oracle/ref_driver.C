@@ -9,7 +9,8 @@
   Usage:
       ref_driver <problem.bin> <out.bin> <op> [args...]
   ops:
-      amul | tmul | suma | residual            -> out = field[nCells]
+      amul | tmul | suma | residual | H | H1   -> out = field[nCells]
+      faceH                                    -> out = field[nFaces]
       precondition <name>                      -> out = M^-1 source
       smooth "<dict text>" <nSweeps>           -> out = psi after sweeps
       solve  "<dict text>"                     -> out = psi; PERF line on stdout
@@ -232,6 +233,18 @@ int main(int argc, char* argv[])
     {
         A.residual(out, psi, source, bouCoeffs, interfaces, 0);
     }
+    else if (op == "H")        // lduMatrixTemplates.C:33-65
+    {
+        out = A.H(psi)();
+    }
+    else if (op == "H1")       // lduMatrixATmul.C:298-327
+    {
+        out = A.H1()();
+    }
+    else if (op == "faceH")    // lduMatrixTemplates.C:79-113: one value per face
+    {
+        out = A.faceH(psi)();
+    }
     else if (op == "precondition" || op == "preconditionT")
     {
         // a solver object is needed to construct a preconditioner
@@ -349,7 +362,7 @@ int main(int argc, char* argv[])
     }
     else
     {
-        fwrite(out.begin(), sizeof(scalar), nCells, g);
+        fwrite(out.begin(), sizeof(scalar), out.size(), g);
     }
     fclose(g);
     return 0;

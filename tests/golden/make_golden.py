@@ -31,6 +31,9 @@ def main():
         out["tmul"] = O.ref_run(s, "tmul", psi=x)[0]
         out["sumA"] = O.ref_run(s, "suma")[0]
         out["residual"] = O.ref_run(s, "residual", psi=x)[0]
+        out["H"] = O.ref_run(s, "H", psi=x)[0]
+        out["H1"] = O.ref_run(s, "H1")[0]
+        out["faceH"] = O.ref_run(s, "faceH", psi=x)[0]
         for pre in cases.PRECONDITIONERS:
             if cases.selectable(s, pre):
                 out[f"pre_{pre}"] = O.ref_run(s, "precondition", pre)[0]

@@ -59,6 +59,11 @@ def test_amul_family_bit_exact(ctx, system):
     assert np.array_equal(A.Tmul(x), w.tmul(x)[0])
     assert np.array_equal(A.sumA(), w.sumA()[0])
     assert np.array_equal(A.residual(x, s["source"]), w.residual(x, s["source"])[0])
+    # the face-loop operators around the solve: H, H1, faceH
+    assert np.array_equal(A.H(x), w.H(x)[0])
+    assert np.array_equal(A.H1(), w.H1()[0])
+    if s["nFaces"]:
+        assert np.array_equal(A.faceH(x), w.faceH(x)[0])
     A.destroy()
 
 

@@ -21,6 +21,9 @@ def test_operators_preconditioners_smoothers(name):
     assert np.array_equal(w.amul(x)[0], g["amul"])
     assert np.array_equal(w.tmul(x)[0], g["tmul"])
     assert np.array_equal(w.sumA()[0], g["sumA"])
+    assert np.array_equal(w.H(x)[0], g["H"])
+    assert np.array_equal(w.H1()[0], g["H1"])
+    assert np.array_equal(w.faceH(x)[0], g["faceH"])
     assert np.array_equal(w.residual(x, s["source"])[0], g["residual"])
     checked = 0
     for key in g.files:

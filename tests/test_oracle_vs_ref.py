@@ -19,6 +19,9 @@ def test_operators(name):
     assert np.array_equal(w.amul(x)[0], O.ref_run(s, "amul", psi=x)[0])
     assert np.array_equal(w.tmul(x)[0], O.ref_run(s, "tmul", psi=x)[0])
     assert np.array_equal(w.sumA()[0], O.ref_run(s, "suma")[0])
+    assert np.array_equal(w.H(x)[0], O.ref_run(s, "H", psi=x)[0])
+    assert np.array_equal(w.H1()[0], O.ref_run(s, "H1")[0])
+    assert np.array_equal(w.faceH(x)[0], O.ref_run(s, "faceH", psi=x)[0])
     assert np.array_equal(w.residual(x, s["source"])[0], O.ref_run(s, "residual", psi=x)[0])
 
 
