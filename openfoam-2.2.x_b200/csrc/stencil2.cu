@@ -40,6 +40,13 @@
 //   TMA bulk chunks + mbarrier per ring slot                                  585   (chunk
 //       boundaries of the planes fall into different ticks again)
 //   cp.async ring, uniform steps, asynchronous helper (this file)             452   (W = 6)
+//   + operands as 32-byte structs (2 x 16-byte cp.async, 2 x LDS.128), loop not unrolled,
+//     role-specialised loops, out-of-line slow paths: 35 instead of 90 instructions per
+//     step, the first CTA runs at 0.20 us per step instead of 0.28 ...          515   (the hops
+//       between CTAs, not the step, set the pace: ~3.7 us per stack, ~17 us per column)
+//   + thread-block clusters of 8 stacks handing over through distributed shared
+//     memory (st.shared::cluster into the next CTA's ring)                  474-493   (two CTAs
+//       per SM and cluster placement slow the first CTA to 0.39 us per step)
 // A tick still costs ~470 cycles (60-70 dependent instructions per step and plane); the
 // barrier + hand-off chain alone is 105.
 #include <algorithm>
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
             for (int q = 0; q < p; q++) tick();   // plane p starts in interval p
 
             StepOps2 o;   // operands of the coming step
-            cp_async_wait<kD - 1>();
+            cp_async_wait<kD - 2>();   // rows of steps 0 and 1: the loop fetches one step ahead
             fetch(0u, o);
             double prev = 0.0;
             // k-neighbour value and j- / i-terms of the coming step.  Step 0 only has the edge
