@@ -753,6 +753,9 @@ int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const d
     Products P;
     LDU_TRY(products_for(m, s, rD, coefF, coefB, &P));
     cudaStream_t st = m->ctx->stream;
+    // the last CTA of a sweep re-arms the ticket itself; a sweep that was aborted half-way (exchange
+    // time-out) would leave it armed wrongly for the next application
+    LDU_CUDA(cudaMemsetAsync(s->ticket, 0, 2 * sizeof(unsigned int), st));
     const int nBlk = (s->b.steps + 31) / 32;
     const int gridT = s->b.nTiles * nBlk;
     if (init) pack2_kernel<true><<<gridT, 256, 0, st>>>(s->b, nBlk, r, rD, s->Y, m->d_scalars);
