@@ -182,6 +182,7 @@ struct ldu_matrix {
     // structured hex box detected from the addressing (nx, ny, nz; 0 = not a box) and
     // the line-pipelined sweep state (stencil.cu)
     int box[3] = {0, 0, 0};
+    int boxDivOk = 0;         // box row kernel: 0 = not checked yet, 1 = usable, -1 = use the generic row kernel
     void* stencil = nullptr;
     void* stencil2 = nullptr;  // plane-stacked second-generation sweeps (stencil2.cu)
     long long coefGen = 0;    // bumped whenever diag/upper/lower change
