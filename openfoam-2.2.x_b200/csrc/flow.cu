@@ -31,6 +31,10 @@
 
 namespace ldu {
 
+#ifndef LDU_FLOW_SLEEP
+#define LDU_FLOW_SLEEP 0
+#endif
+constexpr bool kFlowSleep = LDU_FLOW_SLEEP != 0;
 constexpr long long kFlowTimeout = 4000000000ll;  // ~2 s without progress: bail out loudly
 
 struct LLWord {  // 16 bytes, 16-byte aligned
@@ -56,7 +60,7 @@ __device__ __forceinline__ bool ll_wait(const LLWord* p, unsigned int epoch, dou
                      : "l"(p)
                      : "memory");
         if (f0 == epoch && f1 == epoch) break;
-        __nanosleep(spin < 4 ? 20 : 100);
+        if (kFlowSleep) __nanosleep(spin < 4 ? 20 : 100);
         if ((spin & 1023) == 1023) {
             if (t0 == 0) t0 = clock64();
             else if (clock64() - t0 > kFlowTimeout) {
@@ -114,6 +118,10 @@ __global__ void __launch_bounds__(kBlock) flow_fwd_kernel(FlowArgs a)
         double pc[kPre], pc2[kPre];
         int kBeg = 0, kEnd = 0;
         double acc = 0.0, rDc = 0.0;
+        constexpr bool kGS = (MODE == FLOW_GS || MODE == FLOW_GS_STORE);
+        constexpr int kPreU = kGS ? 6 : 1;
+        double uc[kPreU], uv[kPreU], dg = 1.0;
+        int fU0 = 0, fU1 = 0;
         if (row >= 0) {
             kBeg = a.losortStart[row];
             kEnd = a.losortStart[row + 1];
@@ -133,6 +141,21 @@ __global__ void __launch_bounds__(kBlock) flow_fwd_kernel(FlowArgs a)
                     const double c = a.coef[f];
                     pc[j] = (MODE == FLOW_DIC) ? __dmul_rn(rDc, c) : c;
                     pc2[j] = (MODE == FLOW_RD) ? a.coef2[f] : 0.0;
+                }
+            }
+            if (kGS) {
+                // Gauss-Seidel: the upper part uses values of the PREVIOUS sweep — the rows above
+                // all await this row, so they cannot have been finalised yet and their old values
+                // can be fetched now, off the critical path (only the arithmetic stays in order)
+                fU0 = a.ownerStart[row];
+                fU1 = a.ownerStart[row + 1];
+                dg = a.diag[row];
+#pragma unroll
+                for (int j = 0; j < kPreU; j++) {
+                    if (fU0 + j < fU1) {
+                        uc[j] = a.coef2[fU0 + j];
+                        uv[j] = a.w[a.u[fU0 + j]];
+                    }
                 }
             }
         }
@@ -159,9 +182,12 @@ __global__ void __launch_bounds__(kBlock) flow_fwd_kernel(FlowArgs a)
                 if (MODE == FLOW_GS_STORE) a.bLower[row] = acc;
                 // upper part: values of the previous sweep (rows above cannot have
                 // been finalised yet: they all await this row)
-                for (int f = a.ownerStart[row]; f < a.ownerStart[row + 1]; f++)
+#pragma unroll
+                for (int j = 0; j < kPreU; j++)
+                    if (fU0 + j < fU1) acc = __dsub_rn(acc, __dmul_rn(uc[j], uv[j]));
+                for (int f = fU0 + kPreU; f < fU1; f++)   // cells that own more than kPreU faces
                     acc = __dsub_rn(acc, __dmul_rn(a.coef2[f], a.w[a.u[f]]));
-                acc = __ddiv_rn(acc, a.diag[row]);
+                acc = __ddiv_rn(acc, dg);
             }
             a.w[row] = acc;
             ll_store(a.ll + row, acc, a.epoch);
@@ -188,12 +214,13 @@ __global__ void __launch_bounds__(kBlock) flow_bwd_kernel(FlowArgs a)
         int pcol[kPre];
         double pc[kPre];
         int f0 = 0, fEnd = 0;
-        double acc = 0.0, rDc = 0.0;
+        double acc = 0.0, rDc = 0.0, dg = 1.0;
         if (row >= 0) {
             f0 = a.ownerStart[row];
             fEnd = a.ownerStart[row + 1];
             if (MODE == FLOWB_GS) {
                 acc = a.r[row];
+                dg = a.diag[row];   // before the gate: only the awaited values sit on the critical path
             } else {
                 rDc = a.rD[row];
                 acc = a.w[row];
@@ -227,7 +254,7 @@ __global__ void __launch_bounds__(kBlock) flow_bwd_kernel(FlowArgs a)
                 if (MODE == FLOWB_DIC) acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(rDc, a.coef[f]), v));
                 else acc = __dsub_rn(acc, __dmul_rn(a.coef[f], v));
             }
-            if (MODE == FLOWB_GS) acc = __ddiv_rn(acc, a.diag[row]);
+            if (MODE == FLOWB_GS) acc = __ddiv_rn(acc, dg);
             a.w[row] = acc;
             ll_store(a.ll + row, acc, a.epoch);
         }
