@@ -169,6 +169,13 @@ int ldu_matrix_set_coeffs_device(ldu_matrix* m, const double* d_diag, const doub
 /* faceAreaPair agglomeration weights (finiteVolume/.../faceAreaPairGAMGAgglomeration.C:48-73) */
 int ldu_matrix_set_face_weights(ldu_matrix* m, const double* weights);
 
+/* Colour-ordered renumbering, host only (stands where renumberMesh stands in the reference
+ * tool chain, applications/utilities/mesh/manipulation/renumberMesh): greedy colouring of the cell graph, cells
+ * sorted by (colour, old index).  newIndexOfOldCell[nCells] out; *nColours out (may be NULL).  In that numbering
+ * the reference's lexicographic Gauss-Seidel / DIC sweeps have a dependency depth of nColours. */
+int ldu_colour_order(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr,
+                     int* newIndexOfOldCell, int* nColours);
+
 /* ---- operators: host in / host out ---------------------------------------- */
 /* lduMatrix::Amul  matrices/lduMatrix/lduMatrix/lduMatrixATmul.C:34-92 */
 int ldu_amul(ldu_matrix* m, double* Apsi, const double* psi);

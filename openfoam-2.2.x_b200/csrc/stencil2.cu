@@ -644,7 +644,11 @@ int products_for(ldu_matrix* m, State2* s, const double* rD, const double* coefF
             return LDU_OK;
         }
     }
-    ProductSlot& ps = s->slot[0].lastUse <= s->slot[1].lastUse ? s->slot[0] : s->slot[1];
+    // same arrays, new values (the next solve): recompute in place; otherwise the least recently used slot
+    int pick = s->slot[0].lastUse <= s->slot[1].lastUse ? 0 : 1;
+    for (int q = 0; q < 2; q++)
+        if (s->slot[q].allocated && s->slot[q].rD == rD && s->slot[q].coefF == coefF && s->slot[q].coefB == coefB) pick = q;
+    ProductSlot& ps = s->slot[pick];
     cudaStream_t st = m->ctx->stream;
     if (!ps.allocated) {
         for (int d = 0; d < 3; d++) {
