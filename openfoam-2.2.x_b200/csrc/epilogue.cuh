@@ -27,6 +27,15 @@ __device__ __forceinline__ void push_history(SolverScalars* S)
     S->histCount++;
 }
 
+struct EpiWArA {  // PCG.C:126-132
+    __device__ void operator()(SolverScalars* S, const double* t) const
+    {
+        S->wArAold = S->wArA;
+        S->wArA = t[0];
+        S->beta = __ddiv_rn(S->wArA, S->wArAold);
+    }
+};
+
 // `while (nIterations++ < maxIter && !checkConvergence)` with `inc` added per
 // pass (PCG.C:174-178: inc = 1 post-increment; smoothSolver.C:166-170 and
 // GAMGSolverSolve.C:109-113 pre-increment)

@@ -15,6 +15,7 @@
 // so the host can enqueue iterations in batches and poll rarely while the
 // iteration count and the iterates stay exactly the reference's.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "epilogue.cuh"
@@ -39,15 +40,6 @@ struct EpiNormFactor {  // lduMatrixSolver.C:191-193 + PCG.C:108-112
         S->finalResidual = S->initialResidual;
         push_history(S);
         if (check_convergence(S)) S->done = 1;
-    }
-};
-
-struct EpiWArA {  // PCG.C:126-132
-    __device__ void operator()(SolverScalars* S, const double* t) const
-    {
-        S->wArAold = S->wArA;
-        S->wArA = t[0];
-        S->beta = __ddiv_rn(S->wArA, S->wArAold);
     }
 };
 
@@ -235,6 +227,7 @@ __global__ void init_scalars_kernel(SolverScalars* S, double tol, double relTol,
 int init_scalars(ldu_matrix* m, const ldu_controls* c)
 {
     LDU_TRY(ensure_scalars(m));
+    stencil2_invalidate(m);
     init_scalars_kernel<<<1, 1, 0, m->ctx->stream>>>(m->d_scalars, c->tolerance, c->relTol, c->maxIter, m->d_hist);
     count_launch();
     LDU_CUDA(cudaGetLastError());
@@ -478,6 +471,10 @@ static int krylov_solve(ldu_matrix* m, const ldu_controls* c, double* psi, const
     Precond pre;
     if (!useGamg) LDU_TRY(precond_setup(m, c->preconditioner, pre, W_RD));
     const bool cheap = (c->preconditioner == LDU_PRECOND_NONE || c->preconditioner == LDU_PRECOND_DIAGONAL);
+    // the fused kernels sum in tile order: not for the reference-order verification mode
+    static const bool fuseOff = getenv("LDU_PCG_FUSE") && getenv("LDU_PCG_FUSE")[0] == '0';
+    const bool fusedBox = !bicg && !useGamg && !fuseOff && !m->referenceOrderSums && stencil_version(m) == 2
+                          && (pre.kind == LDU_PRECOND_DIC || pre.kind == LDU_PRECOND_FDIC);
     int interval = c->checkInterval > 0 ? c->checkInterval : (cheap ? 32 : (useGamg ? 1 : 8));
     int enqueued = 0;   // never enqueue more than the maxIter+1 iterations the loop can run
     const double* dotPartner = bicg ? rT : rA;
@@ -495,6 +492,10 @@ static int krylov_solve(ldu_matrix* m, const ldu_controls* c, double* psi, const
             } else if (pre.kind == LDU_PRECOND_DIAGONAL) {
                 rc = launch_map_reduce<1, true>(m, n, DiagPrecondDotMap{wA, pre.rD, rA, dotPartner}, EpiWArA());
                 if (rc == LDU_OK && bicg) rc = precond_apply(m, pre, wT, rT, true);
+            } else if (fusedBox) {
+                // blockMesh box, DIC / FDIC: both substitutions, the way back from the tile layout and
+                // <wA, rA> in one pass (stencil2.cu)
+                rc = stencil2_apply_dot(m, pre.rD, m->d_upper, m->d_upper, rA, wA, rA);
             } else {
                 rc = precond_apply(m, pre, wA, rA, false);
                 if (rc == LDU_OK && bicg) rc = precond_apply(m, pre, wT, rT, true);
@@ -510,8 +511,11 @@ static int krylov_solve(ldu_matrix* m, const ldu_controls* c, double* psi, const
             if (rc == LDU_OK) rc = launch_map_reduce<1, true>(m, n, DotMap{wA, bicg ? pT : pA}, EpiWApA());
             if (rc != LDU_OK) break;
             // psi += alpha pA ; rA -= alpha wA ; residual ; loop test   (PCG.C:166-178)
-            rc = launch_map_reduce<1, true>(m, n, XRUpdateMap{m->d_scalars, psi, rA, pA, wA, rT, wT},
-                                            EpiResidual<true>{1});
+            if (fusedBox)   // ... and the next iteration's rD*rA goes to the tile layout in the same pass
+                rc = stencil2_xr_pack(m, pre.rD, psi, rA, pA, wA);
+            else
+                rc = launch_map_reduce<1, true>(m, n, XRUpdateMap{m->d_scalars, psi, rA, pA, wA, rT, wT},
+                                                EpiResidual<true>{1});
         }
         if (rc != LDU_OK) break;
         rc = read_scalars(m, &hs);

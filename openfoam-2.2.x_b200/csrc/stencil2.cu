@@ -52,6 +52,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "epilogue.cuh"
 #include "reduce.cuh"
 #include "sweeps.h"
 
@@ -508,6 +509,78 @@ __global__ void __launch_bounds__(256) unpack2_kernel(Box2 b, int nBlk, const do
     }
 }
 
+// unpack fused with a dot product: dst = Y (natural order), sum(dst * other) -> epilogue.
+// Persistent over the tile blocks so that the partial sums fit the reduction scratch.
+template <class Epi>
+__global__ void __launch_bounds__(kBlock) unpack2_dot_kernel(Box2 b, int nBlk, int nTileBlocks,
+                                                             const double* __restrict__ Y, double* __restrict__ dst,
+                                                             const double* __restrict__ other, Epi epi, ReduceCtx rc)
+{
+    if (rc.S->done) return;
+    __shared__ double s[32][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double acc[1] = {0.0};
+    for (int tbk = blockIdx.x; tbk < nTileBlocks; tbk += gridDim.x) {
+        const int T = tbk / nBlk, tb = (tbk - T * nBlk) * 32;
+        const int k = T / b.nJ, J = T - k * b.nJ;
+        for (int x = wid; x < 32; x += 8) {
+            const int t = tb + x;
+            s[lane][x] = (t < b.steps) ? Y[((long long)T * b.steps + t) * 32 + lane] : 0.0;
+        }
+        __syncthreads();
+        for (int r = wid; r < 32; r += 8) {
+            const int j = J * 32 + r, i = tb - r + lane;
+            if (j < b.ny && i >= 0 && i < b.nx) {
+                const long long c = ((long long)k * b.ny + j) * b.nx + i;
+                const double v = s[r][lane];
+                dst[c] = v;
+                acc[0] = __dadd_rn(acc[0], __dmul_rn(v, other[c]));
+            }
+        }
+        __syncthreads();
+    }
+    reduce_tail<1>(acc, rc, epi);
+}
+
+// PCG.C:166-172 in tile-block order: psi += alpha pA; rA -= alpha wA; sum |rA| -> epilogue; and
+// Y = rD * rA in tile layout for the next preconditioner application
+template <class Epi>
+__global__ void __launch_bounds__(kBlock) xr_pack2_kernel(Box2 b, int nBlk, int nTileBlocks, double* __restrict__ psi,
+                                                          double* __restrict__ rA, const double* __restrict__ pA,
+                                                          const double* __restrict__ wA, const double* __restrict__ rD,
+                                                          double* __restrict__ Y, Epi epi, ReduceCtx rc)
+{
+    if (rc.S->done) return;
+    __shared__ double s[32][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double alpha = rc.S->alpha;
+    double acc[1] = {0.0};
+    for (int tbk = blockIdx.x; tbk < nTileBlocks; tbk += gridDim.x) {
+        const int T = tbk / nBlk, tb = (tbk - T * nBlk) * 32;
+        const int k = T / b.nJ, J = T - k * b.nJ;
+        for (int r = wid; r < 32; r += 8) {
+            const int j = J * 32 + r, i = tb - r + lane;
+            double v = 0.0;
+            if (j < b.ny && i >= 0 && i < b.nx) {
+                const long long c = ((long long)k * b.ny + j) * b.nx + i;
+                psi[c] = __dadd_rn(psi[c], __dmul_rn(alpha, pA[c]));
+                const double rr = __dsub_rn(rA[c], __dmul_rn(alpha, wA[c]));
+                rA[c] = rr;
+                acc[0] = __dadd_rn(acc[0], fabs(rr));
+                v = __dmul_rn(rD[c], rr);
+            }
+            s[r][lane] = v;
+        }
+        __syncthreads();
+        for (int x = wid; x < 32; x += 8) {
+            const int t = tb + x;
+            if (t < b.steps) Y[((long long)T * b.steps + t) * 32 + lane] = s[lane][x];
+        }
+        __syncthreads();
+    }
+    reduce_tail<1>(acc, rc, epi);
+}
+
 // premultiplied coefficients in tile layout: F* for the forward sweep (lower faces of a
 // cell, neighbour order k-, j-, i-), B* for the backward one (upper faces, k+, j+, i+)
 struct Products {
@@ -567,6 +640,7 @@ struct State2 {
     ProductSlot slot[2];
     long long useClock = 0;
     bool attrSet = false;
+    const double* yReadyFor = nullptr;   // Y already holds rD * (this vector), written by xr_pack2_kernel
     unsigned long long* trace = nullptr;
 };
 
@@ -749,8 +823,8 @@ void stencil2_free(ldu_matrix* m)
 // w = backward(forward(init ? rD*r : w)): both substitutions of a DIC / DILU / FDIC
 // application.  coefF multiplies the lower faces in the forward sweep, coefB the upper
 // faces in the backward sweep (DIC: upper/upper, DILU: lower/upper, DILU^T: upper/lower).
-int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, const double* r,
-                   double* w, bool init)
+static int apply_core(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, const double* r,
+                      double* w, bool init, const double* dotWith)
 {
     State2* s;
     LDU_TRY(state2(m, &s));
@@ -762,10 +836,15 @@ int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const d
     LDU_CUDA(cudaMemsetAsync(s->ticket, 0, 2 * sizeof(unsigned int), st));
     const int nBlk = (s->b.steps + 31) / 32;
     const int gridT = s->b.nTiles * nBlk;
-    if (init) pack2_kernel<true><<<gridT, 256, 0, st>>>(s->b, nBlk, r, rD, s->Y, m->d_scalars);
-    else pack2_kernel<false><<<gridT, 256, 0, st>>>(s->b, nBlk, w, nullptr, s->Y, m->d_scalars);
-    count_launch();
-    LDU_CUDA(cudaGetLastError());
+    if (init && s->yReadyFor == r && r != nullptr) {
+        // xr_pack2_kernel has already left rD * r in the tile layout
+    } else {
+        if (init) pack2_kernel<true><<<gridT, 256, 0, st>>>(s->b, nBlk, r, rD, s->Y, m->d_scalars);
+        else pack2_kernel<false><<<gridT, 256, 0, st>>>(s->b, nBlk, w, nullptr, s->Y, m->d_scalars);
+        count_launch();
+        LDU_CUDA(cudaGetLastError());
+    }
+    s->yReadyFor = nullptr;
     S2Args a;
     a.S = m->d_scalars;
     a.guarded = 1;
@@ -781,10 +860,47 @@ int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const d
     else if (s->W == 3) LDU_TRY(launch_sweeps<3>(m, s, a, P));
     else if (s->W == 2) LDU_TRY(launch_sweeps<2>(m, s, a, P));
     else LDU_TRY(launch_sweeps<4>(m, s, a, P));
-    unpack2_kernel<<<gridT, 256, 0, st>>>(s->b, nBlk, s->Y, w, m->d_scalars);
+    if (dotWith) {
+        unpack2_dot_kernel<<<grid_for(m->ctx, m->nCells), kBlock, 0, st>>>(s->b, nBlk, gridT, s->Y, w, dotWith, EpiWArA(),
+                                                                          make_rc(m));
+    } else {
+        unpack2_kernel<<<gridT, 256, 0, st>>>(s->b, nBlk, s->Y, w, m->d_scalars);
+    }
     count_launch();
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;
+}
+
+int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, const double* r,
+                   double* w, bool init)
+{
+    return apply_core(m, rD, coefF, coefB, r, w, init, nullptr);
+}
+
+int stencil2_apply_dot(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, const double* r,
+                       double* w, const double* dotWith)
+{
+    return apply_core(m, rD, coefF, coefB, r, w, true, dotWith);
+}
+
+int stencil2_xr_pack(ldu_matrix* m, const double* rD, double* psi, double* rA, const double* pA, const double* wA)
+{
+    State2* s;
+    LDU_TRY(state2(m, &s));
+    const int nBlk = (s->b.steps + 31) / 32;
+    const int nTileBlocks = s->b.nTiles * nBlk;
+    xr_pack2_kernel<<<grid_for(m->ctx, m->nCells), kBlock, 0, m->ctx->stream>>>(s->b, nBlk, nTileBlocks, psi, rA, pA, wA, rD,
+                                                                               s->Y, EpiResidual<true>{1}, make_rc(m));
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    s->yReadyFor = rA;
+    return LDU_OK;
+}
+
+void stencil2_invalidate(ldu_matrix* m)
+{
+    State2* s = reinterpret_cast<State2*>(m->stencil2);
+    if (s) s->yReadyFor = nullptr;
 }
 
 }  // namespace ldu

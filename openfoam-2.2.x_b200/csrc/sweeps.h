@@ -34,6 +34,13 @@ void stencil2_free(ldu_matrix* m);
 int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, const double* r,
                    double* w, bool init);
 
+// PCG on a box (solvers.cu): the application fused with <w, dotWith> (EpiWArA), and the x/r update
+// fused with |r|_1 (EpiResidual) and with the packing of rD*rA for the next application
+int stencil2_apply_dot(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, const double* r,
+                       double* w, const double* dotWith);
+int stencil2_xr_pack(ldu_matrix* m, const double* rD, double* psi, double* rA, const double* pA, const double* wA);
+void stencil2_invalidate(ldu_matrix* m);   // the tile image of rD*rA is stale (a new solve starts)
+
 // forward then backward substitution: w = B^-1 F^-1 (init ? rD*r : w)
 int sweep_pair(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, bool pre,
                const double* r, double* w, bool init);
