@@ -47,6 +47,9 @@
 //   + thread-block clusters of 8 stacks handing over through distributed shared
 //     memory (st.shared::cluster into the next CTA's ring)                  474-493   (two CTAs
 //       per SM and cluster placement slow the first CTA to 0.39 us per step)
+//   + helper forwarding the j-words of all planes with one load (lane = plane x row), 6 k-rows
+//     per round trip, optionally split into a k-helper and a j-helper warp     472-477   (column
+//       hops 13 instead of 17-25 us, stack hops 5.5 instead of 3.7 us: no net gain)
 // A tick still costs ~470 cycles (60-70 dependent instructions per step and plane); the
 // barrier + hand-off chain alone is 105.
 #include <algorithm>
