@@ -323,6 +323,13 @@ def run_ours(args):
                              "for arbitrary LDU addressing on the same matrix",
                      "generic": {"kernel": "row_kernel<0,1,8>", "achieved": amul_generic_gbs,
                                  "frac": amul_generic_gbs / peak, "amul_ms": ms_amul_generic, "traffic": None}},
+        # the whole PCG iteration against the same roofline: unfused algorithmic bytes of SURVEY.md 8d
+        # (352 B/cell/iteration with DIC, 208 with diagonal) x cells of all regions x iterations/s, per GPU
+        "pcg_roofline": {"alg_bytes_per_cell_iter": 352 if args.precond == "DIC" else 208,
+                         "achieved_gbs_per_gpu": value * (352 if args.precond == "DIC" else 208) * n ** 3 / 1e9 / world,
+                         "frac": value * (352 if args.precond == "DIC" else 208) * n ** 3 / 1e9 / world / peak,
+                         "bound": "dependency chain of the DIC sweeps (nx+ny+nz-2 hyperplanes per sweep), not HBM"
+                                  if args.precond == "DIC" else "hbm"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "gpu_launches": int(launches),
