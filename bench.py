@@ -285,8 +285,10 @@ def run_ours(args):
     h_src = ldub200.pinned_array(nC); h_src[:] = reg["source"]
     h_psi = ldub200.pinned_array(nC)
 
+    import ctypes
+
     def step_e2e():
-        h_psi[:] = 0.0
+        ctypes.memset(h_psi.ctypes.data, 0, h_psi.nbytes)   # psi0 = 0 (libc memset; numpy's fill is 3x slower)
         A.set_coeffs(h_diag, h_upper, None, bou, inc)
         perf = solver.solve(h_psi, h_src)
         assert perf.nIterations == args.iters

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "epilogue.cuh"
 #include "reduce.cuh"
 
 namespace ldu {
@@ -199,6 +200,45 @@ __global__ void __launch_bounds__(kBlock, MINB) box_row_kernel(int n, BoxView v,
         acc = row_term<MODE>(acc, ak, xK, hasK);
         y[c] = acc;
     }
+}
+
+// Amul on a box fused with <A x, x> (PCG.C:153-155) and the alpha epilogue: the products y[c]*x[c] are
+// summed per thread in row order, then through the fixed-shape reduction of reduce.cuh
+template <class Epi>
+__global__ void __launch_bounds__(kBlock, 6) box_amul_dot_kernel(int n, BoxView v, double* __restrict__ y,
+                                                                  const double* __restrict__ x, Epi epi, ReduceCtx rc)
+{
+    if (rc.S->done) return;
+    const int nx = v.nx, ny = v.ny, nz = v.nz, nxy = nx * ny;
+    double dot[1] = {0.0};
+    for (int c = blockIdx.x * kBlock + threadIdx.x; c < n; c += gridDim.x * kBlock) {
+        const int jk = (int)__umulhi((unsigned int)c, v.mulNx);
+        const int i = c - jk * nx;
+        const int k = (int)__umulhi((unsigned int)jk, v.mulNy);
+        const int j = jk - k * ny;
+        const bool hasI = i < nx - 1, hasJ = j < ny - 1, hasK = k < nz - 1;
+        const int os = box_owner_start(v, c, i, j, k);
+        const int fk = k > 0 ? box_owner_start(v, c - nxy, i, j, k - 1) + hasI + hasJ : 0;
+        const int fj = j > 0 ? box_owner_start(v, c - nx, i, j - 1, k) + hasI : 0;
+        const int fi = i > 0 ? box_owner_start(v, c - 1, i - 1, j, k) : 0;
+        const double d = v.diag[c], xc = x[c];
+        const double bk = k > 0 ? v.lowerCoef[fk] : 0.0, xk = k > 0 ? x[c - nxy] : 0.0;
+        const double bj = j > 0 ? v.lowerCoef[fj] : 0.0, xj = j > 0 ? x[c - nx] : 0.0;
+        const double bi = i > 0 ? v.lowerCoef[fi] : 0.0, xi = i > 0 ? x[c - 1] : 0.0;
+        const double ai = hasI ? v.upperCoef[os] : 0.0, xI = hasI ? x[c + 1] : 0.0;
+        const double aj = hasJ ? v.upperCoef[os + hasI] : 0.0, xJ = hasJ ? x[c + nx] : 0.0;
+        const double ak = hasK ? v.upperCoef[os + hasI + hasJ] : 0.0, xK = hasK ? x[c + nxy] : 0.0;
+        double acc = __dmul_rn(d, xc);
+        acc = row_term<0>(acc, bk, xk, k > 0);
+        acc = row_term<0>(acc, bj, xj, j > 0);
+        acc = row_term<0>(acc, bi, xi, i > 0);
+        acc = row_term<0>(acc, ai, xI, hasI);
+        acc = row_term<0>(acc, aj, xJ, hasJ);
+        acc = row_term<0>(acc, ak, xK, hasK);
+        y[c] = acc;
+        dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xc));
+    }
+    reduce_tail<1>(dot, rc, epi);
 }
 
 // exact c / d by multiply-high for every 0 <= c < limit?  (checked on the host, once per matrix)
@@ -566,6 +606,47 @@ int k_faceH(ldu_matrix* m, double* faceHpsi, const double* psi)
     if (m->nFaces <= 0) return LDU_OK;
     faceH_kernel<<<grid_for(m->ctx, m->nFaces), kBlock, 0, m->ctx->stream>>>(m->nFaces, m->d_l, m->d_u, m->d_lower,
                                                                             m->d_upper, psi, faceHpsi);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+static bool box_view(ldu_matrix* m, const RowView& v, BoxView& bv)
+{
+    const char* boxEnv = getenv("LDU_AMUL_BOX");
+    if (m->box[0] <= 0 || (boxEnv && boxEnv[0] == '0') || m->boxDivOk < 0) return false;
+    const int n = m->nCells;
+    const unsigned int mulNx = (unsigned int)((0x100000000ull + m->box[0] - 1) / m->box[0]);
+    const unsigned int mulNy = (unsigned int)((0x100000000ull + m->box[1] - 1) / m->box[1]);
+    if (m->boxDivOk == 0) {   // first use: are the multiply-high divisions exact for this box?
+        const bool ok = m->box[0] > 1 && m->box[1] > 1 && magic_div_ok(m->box[0], mulNx, (unsigned int)n)
+                        && magic_div_ok(m->box[1], mulNy, (unsigned int)(n / m->box[0]) + 1u);
+        m->boxDivOk = ok ? 1 : -1;
+    }
+    if (m->boxDivOk != 1) return false;
+    bv.nx = m->box[0];
+    bv.ny = m->box[1];
+    bv.nz = m->box[2];
+    bv.mulNx = mulNx;
+    bv.mulNy = mulNy;
+    bv.diag = v.diag;
+    bv.lowerCoef = v.lowerCoef;
+    bv.upperCoef = v.upperCoef;
+    return true;
+}
+
+bool k_amul_dot_available(ldu_matrix* m)
+{
+    BoxView bv;
+    return m->nIfFaces == 0 && m->ctx->comm.nRanks == 1 && m->nCells > 0 && box_view(m, row_view(m, false), bv);
+}
+
+int k_amul_dot(ldu_matrix* m, double* Apsi, const double* psi)
+{
+    BoxView bv;
+    if (!box_view(m, row_view(m, false), bv)) return LDU_EINVAL;
+    box_amul_dot_kernel<<<grid_for(m->ctx, m->nCells), kBlock, 0, m->ctx->stream>>>(m->nCells, bv, Apsi, psi, EpiWApA(),
+                                                                               make_rc(m));
     count_launch();
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;

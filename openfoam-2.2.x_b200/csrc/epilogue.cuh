@@ -36,6 +36,21 @@ struct EpiWArA {  // PCG.C:126-132
     }
 };
 
+struct EpiWApA {  // PCG.C:155-164
+    __device__ void operator()(SolverScalars* S, const double* t) const
+    {
+        S->wApA = t[0];
+        // checkSingularity(mag(wApA)/normFactor): SolverPerformance.C:31-43
+        if (__ddiv_rn(fabs(S->wApA), S->normFactor) < kVSmall) {
+            S->singular = 1;
+            S->done = 1;
+        } else {
+            S->singular = 0;
+            S->alpha = __ddiv_rn(S->wArA, S->wApA);
+        }
+    }
+};
+
 // `while (nIterations++ < maxIter && !checkConvergence)` with `inc` added per
 // pass (PCG.C:174-178: inc = 1 post-increment; smoothSolver.C:166-170 and
 // GAMGSolverSolve.C:109-113 pre-increment)

@@ -236,6 +236,9 @@ int k_amul(ldu_matrix* m, double* Apsi, const double* psi, bool transpose, bool 
 int k_interfaces(ldu_matrix* m, double* result, const double* psi, int whichCoeffs, double sign,
                  bool guarded = false);
 int k_sumA(ldu_matrix* m, double* sumA);
+// PCG on a single-region box: Apsi = A psi fused with <Apsi, psi> and the alpha epilogue (guarded)
+bool k_amul_dot_available(ldu_matrix* m);
+int k_amul_dot(ldu_matrix* m, double* Apsi, const double* psi);
 int k_H(ldu_matrix* m, double* Hpsi, const double* psi);        // lduMatrix::H
 int k_H1(ldu_matrix* m, double* H1);                             // lduMatrix::H1
 int k_faceH(ldu_matrix* m, double* faceHpsi, const double* psi);  // lduMatrix::faceH (face-sized output)

@@ -43,21 +43,6 @@ struct EpiNormFactor {  // lduMatrixSolver.C:191-193 + PCG.C:108-112
     }
 };
 
-struct EpiWApA {  // PCG.C:155-164
-    __device__ void operator()(SolverScalars* S, const double* t) const
-    {
-        S->wApA = t[0];
-        // checkSingularity(mag(wApA)/normFactor): SolverPerformance.C:31-43
-        if (__ddiv_rn(fabs(S->wApA), S->normFactor) < kVSmall) {
-            S->singular = 1;
-            S->done = 1;
-        } else {
-            S->singular = 0;
-            S->alpha = __ddiv_rn(S->wArA, S->wApA);
-        }
-    }
-};
-
 // ---------------------------------------------------------------------------
 // element-wise maps
 // ---------------------------------------------------------------------------
@@ -473,6 +458,7 @@ static int krylov_solve(ldu_matrix* m, const ldu_controls* c, double* psi, const
     const bool cheap = (c->preconditioner == LDU_PRECOND_NONE || c->preconditioner == LDU_PRECOND_DIAGONAL);
     // the fused kernels sum in tile order: not for the reference-order verification mode
     static const bool fuseOff = getenv("LDU_PCG_FUSE") && getenv("LDU_PCG_FUSE")[0] == '0';
+    const bool amulDot = !bicg && !fuseOff && !m->referenceOrderSums && k_amul_dot_available(m);
     const bool fusedBox = !bicg && !useGamg && !fuseOff && !m->referenceOrderSums && stencil_version(m) == 2
                           && (pre.kind == LDU_PRECOND_DIC || pre.kind == LDU_PRECOND_FDIC);
     int interval = c->checkInterval > 0 ? c->checkInterval : (cheap ? 32 : (useGamg ? 1 : 8));
@@ -506,9 +492,13 @@ static int krylov_solve(ldu_matrix* m, const ldu_controls* c, double* psi, const
             rc = launch_map<true>(m, n, PUpdateMap{m->d_scalars, pA, wA, pT, wT});
             if (rc != LDU_OK) break;
             // wA = A pA ; wApA = <wA, pA>            (PCG.C:153-155)
-            rc = k_amul(m, wA, pA, false, true);
-            if (rc == LDU_OK && bicg) rc = k_amul(m, wT, pT, true, true);
-            if (rc == LDU_OK) rc = launch_map_reduce<1, true>(m, n, DotMap{wA, bicg ? pT : pA}, EpiWApA());
+            if (amulDot) {
+                rc = k_amul_dot(m, wA, pA);   // box, one region: wA = A pA and <wA, pA> in one pass
+            } else {
+                rc = k_amul(m, wA, pA, false, true);
+                if (rc == LDU_OK && bicg) rc = k_amul(m, wT, pT, true, true);
+                if (rc == LDU_OK) rc = launch_map_reduce<1, true>(m, n, DotMap{wA, bicg ? pT : pA}, EpiWApA());
+            }
             if (rc != LDU_OK) break;
             // psi += alpha pA ; rA -= alpha wA ; residual ; loop test   (PCG.C:166-178)
             if (fusedBox)   // ... and the next iteration's rD*rA goes to the tile layout in the same pass
