@@ -103,20 +103,30 @@ def measured_peak():
 # reference arm / CPU baseline: the unmodified reference compiled into oracle/_ref
 # --------------------------------------------------------------------------- #
 def reference_cores():
-    """Host cores the reference arm uses: the reference is single-threaded per rank and there is
-    no MPI on this box, so the arm runs one reference process per block of the decomposed box,
-    concurrently (throughput mode), on up to 8 cores."""
+    """Host cores the reference arm uses: the reference is single-threaded per rank, so the arm
+    runs it the way OpenFOAM is run on a multi-core host — the box decomposed into one mesh region
+    per core, one reference process per region, coupled through processor interfaces — on up to
+    8 cores.  This image has no MPI: the reference's Pstream seam is served by
+    oracle/pstream_shm (shared memory) instead of src/Pstream/mpi."""
     c = os.cpu_count() or 1
     return 8 if c >= 8 else 4 if c >= 4 else 2 if c >= 2 else 1
 
 
+def reference_mode(cores):
+    from oracle import oracle as O
+    if cores == 1:
+        return "single"
+    return "coupled" if O.ref_par_available() else "blocks"
+
+
 def reference_rate(n, precond, it_a, it_b, keep=None, cores=None):
-    """Steady-state PCG iterations/s of the reference on the n^3 box split into `cores` blocks,
-    one unmodified reference process per block running concurrently on its own core, block-local
-    DIC, no halo exchange: every coupled iteration of an MPI-parallel reference on that many cores
-    costs at least this much, so the slowest block's rate is an UPPER bound of what the reference
-    would reach there (cores = 1: the plain single-rank reference).  Returns (rate, kind, cpu
-    seconds, cores)."""
+    """Steady-state PCG iterations/s of the reference on the n^3 box on `cores` host cores.
+    cores == 1: the plain single-rank reference.  cores > 1: the box decomposed into `cores`
+    regions, one unmodified reference process per region, coupled (halo exchange through the
+    processor interfaces, global sums through the Pstream seam) exactly as a decomposePar'd
+    case runs; block-local DIC as in the reference.  Fallback when the multi-rank driver did not
+    travel: the same blocks run concurrently but uncoupled (an upper bound of the coupled rate).
+    Returns (rate, kind, cpu seconds, cores)."""
     from concurrent.futures import ThreadPoolExecutor
     from ldub200 import meshes, decompose
     from oracle import oracle as O
@@ -129,15 +139,24 @@ def reference_rate(n, precond, it_a, it_b, keep=None, cores=None):
                   else [decompose.local_box_region(n, r, cores) for r in range(cores)])
         if keep is not None:
             keep[key] = blocks
+    ctl = O.dict_text(dict(solver="PCG", preconditioner=precond))
+
+    def iters_line(so):
+        t = [x for x in so.splitlines() if x.startswith("ITERS")][0].split()
+        return int(t[1]), float(t[2]), int(t[3]), float(t[4])
+
+    if reference_mode(cores) == "coupled":
+        _, so = O.ref_run_par(blocks, "time_iters", ctl, it_a - 1, it_b - 1)
+        ia, ta, ib, tb = iters_line(so)
+        return (ib - ia) / (tb - ta), "reference", (tb + ta) * cores, cores
 
     def one(s):
         if O.ref_available():
-            _, so = O.ref_run(s, "time_iters", O.dict_text(dict(solver="PCG", preconditioner=precond)),
-                              it_a - 1, it_b - 1)
-            t = [x for x in so.splitlines() if x.startswith("ITERS")][0].split()
-            ia, ta, ib, tb = int(t[1]), float(t[2]), int(t[3]), float(t[4])
+            ia, ta, ib, tb = iters_line(O.ref_run({k: v for k, v in s.items() if k != "interfaces"},
+                                                  "time_iters", ctl, it_a - 1, it_b - 1)[1])
             return (ib - ia) / (tb - ta), "reference", tb + ta
         # restatement (oracle/ldu_oracle.c) when the compiled reference did not travel
+        s = {k: v for k, v in s.items() if k != "interfaces"}
         w = O.World([s])
         t0 = time.perf_counter()
         w.solve(controls(precond, it_a), s["psi0"], s["source"])
@@ -149,6 +168,19 @@ def reference_rate(n, precond, it_a, it_b, keep=None, cores=None):
     with ThreadPoolExecutor(max_workers=cores) as ex:
         res = list(ex.map(one, blocks))
     return min(r[0] for r in res), res[0][1], sum(r[2] for r in res), cores
+
+
+def reference_sample(n, precond, iters, cores):
+    mode = reference_mode(cores)
+    if mode == "single":
+        return f"{iters} steady-state iterations of the plain single-rank reference on the whole {n}^3 system"
+    if mode == "coupled":
+        return (f"{iters} steady-state iterations of the {n}^3 system decomposed into {cores} regions, one "
+                f"unmodified reference process per region and core, coupled through processor interfaces over "
+                f"the shared-memory Pstream (oracle/pstream_shm; no MPI in this image), block-local {precond}; "
+                f"two fixed-iteration solves, the difference removes set-up")
+    return (f"{iters} steady-state iterations of the {n}^3 system split into {cores} blocks, one reference "
+            f"process per block and core, concurrently, no halo exchange (upper bound of the coupled rate)")
 
 
 def run_reference(args):
@@ -164,10 +196,7 @@ def run_reference(args):
         if i >= args.warmup:
             rates.append(r)
     value = float(np.mean(rates))
-    sample = (f"{args.ref_iters} steady-state iterations per step of the {args.n}^3 system split into {cores} "
-              f"block(s), one unmodified reference process per block and core, concurrently, block-local "
-              f"{args.precond}, no halo exchange (upper bound of an MPI-parallel reference on {cores} cores; "
-              f"two fixed-iteration solves per process, difference removes set-up)")
+    sample = "per step: " + reference_sample(args.n, args.precond, args.ref_iters, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ref_iters / value,
@@ -351,13 +380,11 @@ def run_ours(args):
             v, kind, spent, cores = reference_rate(n, args.precond, 2, 2 + args.ref_iters)
             v1, _, spent1, _ = reference_rate(n, args.precond, 2, 2 + args.ref_iters, cores=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": f"{args.ref_iters} steady-state iterations of the {n}^3 system split into "
-                                              f"{cores} blocks, one reference process per block and core, concurrently, "
-                                              f"no halo exchange: upper bound of an MPI-parallel reference "
-                                              f"({spent:.1f} s of CPU work)",
+                                    "sample": reference_sample(n, args.precond, args.ref_iters, cores)
+                                              + f" ({spent:.1f} s of CPU work)",
                                     "single_rank": {"value": v1, "cores": 1,
-                                                    "sample": f"the plain single-rank reference on the whole system "
-                                                              f"({spent1:.1f} s of CPU work)"}}
+                                                    "sample": reference_sample(n, args.precond, args.ref_iters, 1)
+                                                              + f" ({spent1:.1f} s of CPU work)"}}
         except Exception as e:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": reference_cores(), "kind": "reference",
                                     "sample": f"failed: {e}"}

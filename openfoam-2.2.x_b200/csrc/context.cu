@@ -413,6 +413,7 @@ int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lower
         LDU_TRY(upload(ctx, &m->d_bRowCell, rowCell.data(), rowCell.size()));
         LDU_TRY(upload(ctx, &m->d_bRowStart, rowStart.data(), rowStart.size()));
         LDU_TRY(upload(ctx, &m->d_bEntry, order.data(), order.size()));
+        m->ifBlockStart = rowCell.front();   // boundary rows are sorted by cell
     }
     LDU_TRY(ensure_scalars(m));
     LDU_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -452,6 +453,7 @@ int ldu_matrix_destroy(ldu_matrix* m)
     cudaFree(m->d_bRowCell);
     cudaFree(m->d_bRowStart);
     cudaFree(m->d_bEntry);
+    cudaFree(m->d_cellBRow);
     flow_free(m);
     stencil_free(m);
     stencil2_free(m);

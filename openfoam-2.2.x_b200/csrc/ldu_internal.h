@@ -171,6 +171,8 @@ struct ldu_matrix {
     int* d_bRowCell = nullptr;     // [nBRows]
     int* d_bRowStart = nullptr;    // [nBRows+1]
     int* d_bEntry = nullptr;       // [nIfFaces] index into the concatenated arrays
+    int ifBlockStart = 0;          // first cell on any interface (nonBlockingGaussSeidelSmoother.C:66-81)
+    int* d_cellBRow = nullptr;     // [nCells] boundary row of a cell or -1 (lazy, nonBlockingGaussSeidel only)
     // sweep schedules (lazy)
     ldu::Schedule fwd, bwd;
     bool haveSchedules = false;

@@ -382,6 +382,20 @@ static int gs_apply(ldu_matrix* m, double* psi, const double* source, int nSweep
     return LDU_OK;
 }
 
+// nonBlockingGaussSeidelSmoother.C:128-217.  Without interfaces it is GaussSeidel; with them the
+// interface terms enter a coupled row between the lower entries from cells below blockStart and
+// the rest (a different rounding order), see nbgs_level_kernel.
+static int nbgs_apply(ldu_matrix* m, double* psi, const double* source, int nSweeps)
+{
+    if (!m->nIfFaces) return gs_apply(m, psi, source, nSweeps, false);
+    for (int sweep = 0; sweep < nSweeps; sweep++) {
+        LDU_TRY(comm_halo_put(m, psi, true));
+        LDU_TRY(comm_halo_recv(m, true));
+        LDU_TRY(nbgs_sweep(m, source, psi));
+    }
+    return LDU_OK;
+}
+
 // DICSmoother.C:67-116, DILUSmoother.C:67-119, FDICSmoother.C:98-146
 static int dic_apply(ldu_matrix* m, const Smoother& s, double* psi, const double* source, int nSweeps)
 {
@@ -405,8 +419,9 @@ int smoother_apply(ldu_matrix* m, const Smoother& s, double* psi, const double* 
 {
     switch (s.kind) {
     case LDU_SMOOTHER_GS:
-    case LDU_SMOOTHER_NBGS:  // nonBlockingGaussSeidelSmoother.C:46-240: same arithmetic
         return gs_apply(m, psi, source, nSweeps, false);
+    case LDU_SMOOTHER_NBGS:
+        return nbgs_apply(m, psi, source, nSweeps);
     case LDU_SMOOTHER_SYMGS:
         return gs_apply(m, psi, source, nSweeps, true);
     case LDU_SMOOTHER_DIC:

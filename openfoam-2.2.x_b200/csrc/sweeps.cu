@@ -180,6 +180,49 @@ __global__ void __launch_bounds__(kBlock) gs_bwd_level_kernel(
     psi[c] = __ddiv_rn(acc, diag[c]);
 }
 
+// nonBlockingGaussSeidelSmoother.C:128-217 on a region with interfaces.  The reference sweeps
+// the cells below blockStart, THEN consumes the interface update, then sweeps the rest, so a
+// coupled row sees: source, lower entries from cells < blockStart, its interface terms (patch
+// order, then face order), lower entries from cells >= blockStart, upper entries.  One level of
+// the forward schedule per launch (the halo has arrived before the first one).
+__global__ void __launch_bounds__(kBlock) nbgs_level_kernel(
+    const SolverScalars* S, const int* __restrict__ rows, int nRows, const int* __restrict__ losortStart,
+    const int* __restrict__ losort, const int* __restrict__ lowerCol, const int* __restrict__ ownerStart,
+    const int* __restrict__ u, const double* __restrict__ diag, const double* __restrict__ upper,
+    const double* __restrict__ lower, const double* __restrict__ source, int blockStart,
+    const int* __restrict__ cellBRow, const int* __restrict__ bRowStart, const int* __restrict__ bEntry,
+    const double* __restrict__ bou, const double* __restrict__ recv, double* __restrict__ psi)
+{
+    if (S->done) return;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nRows) return;
+    const int c = rows[i];
+    double acc = source[c];
+    int br = c >= blockStart ? cellBRow[c] : -1;
+    for (int k = losortStart[c]; k < losortStart[c + 1]; k++) {
+        const int col = lowerCol[k];
+        if (br >= 0 && col >= blockStart) {
+            for (int e = bRowStart[br]; e < bRowStart[br + 1]; e++)
+                acc = __dsub_rn(acc, __dmul_rn(-bou[bEntry[e]], recv[bEntry[e]]));
+            br = -1;
+        }
+        acc = __dsub_rn(acc, __dmul_rn(lower[losort[k]], psi[col]));
+    }
+    if (br >= 0)
+        for (int e = bRowStart[br]; e < bRowStart[br + 1]; e++)
+            acc = __dsub_rn(acc, __dmul_rn(-bou[bEntry[e]], recv[bEntry[e]]));
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++)
+        acc = __dsub_rn(acc, __dmul_rn(upper[f], psi[u[f]]));
+    psi[c] = __ddiv_rn(acc, diag[c]);
+}
+
+__global__ void __launch_bounds__(kBlock) cell_brow_kernel(int nBRows, const int* __restrict__ bRowCell,
+                                                           int* __restrict__ cellBRow)
+{
+    const int r = blockIdx.x * kBlock + threadIdx.x;
+    if (r < nBRows) cellBRow[bRowCell[r]] = r;
+}
+
 #define LEVEL_LOOP(sched, body)                                             \
     for (int L = 0; L < (sched).nLevels; L++) {                             \
         const int start = (sched).levelStart[L];                            \
@@ -326,6 +369,25 @@ int gs_sweep(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, b
                                m->d_ownerStart, m->d_u, m->d_diag, m->d_upper, m->d_lower, bPrime, nullptr,
                                psi)));
     }
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+int nbgs_sweep(ldu_matrix* m, const double* source, double* psi)
+{
+    LDU_TRY(build_schedules(m));
+    cudaStream_t st = m->ctx->stream;
+    if (!m->d_cellBRow) {
+        LDU_CUDA(cudaMalloc((void**)&m->d_cellBRow, std::max(m->nCells, 1) * sizeof(int)));
+        LDU_CUDA(cudaMemsetAsync(m->d_cellBRow, 0xff, std::max(m->nCells, 1) * sizeof(int), st));
+        cell_brow_kernel<<<(m->nBRows + kBlock - 1) / kBlock, kBlock, 0, st>>>(m->nBRows, m->d_bRowCell,
+                                                                              m->d_cellBRow);
+    }
+    LEVEL_LOOP(m->fwd, (nbgs_level_kernel<<<grid, kBlock, 0, st>>>(
+                           m->d_scalars, rows, nRows, m->d_losortStart, m->d_losort, m->d_lowerCol,
+                           m->d_ownerStart, m->d_u, m->d_diag, m->d_upper, m->d_lower, source,
+                           m->ifBlockStart, m->d_cellBRow, m->d_bRowStart, m->d_bEntry, m->d_bou, m->d_recv,
+                           psi)));
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;
 }

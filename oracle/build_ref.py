@@ -14,6 +14,13 @@ libraries the lduMatrix path needs:
                                     see src/OpenFOAM/Make/options)
   src/Pstream/dummy/Make/files     (serial Pstream stubs)
 
+and, for multi-rank runs of the reference without MPI (absent in this image),
+  oracle/_ref/libPstream_shm.so    oracle/pstream_shm/*.C: the Pstream seam over shared
+                                   memory.  Like the reference's own libPstream (dummy vs mpi,
+                                   picked by LD_LIBRARY_PATH) it interposes on the stubs:
+                                   ref_driver_par lists it before libOpenFOAM.so, which stays
+                                   the unmodified serial build.
+
 with the flags of wmake/rules/linux64Gcc/{c++,c++Opt,general}:
   g++ -m64 -Dlinux64 -DWM_DP -DNoRepository -ftemplate-depth-100 -O3 -fPIC
 
@@ -103,25 +110,10 @@ def make_lninclude(dst: Path, roots):
                         link.symlink_to(Path(dirpath) / fn)
 
 
-def main():
-    if not REF.exists():
-        print(f"[build_ref] {REF} absent: using prebuilt oracle/_ref if any")
-        return 0 if (OUT / "libOpenFOAM.so").exists() else 1
-    if (OUT / "libOpenFOAM.so").exists() and "--force" not in sys.argv:
-        print("[build_ref] oracle/_ref/libOpenFOAM.so present (use --force to rebuild)")
-        ln = BUILD / "lnInclude"
-        drv = OUT / "ref_driver"
-        src = HERE / "ref_driver.C"
-        if ln.exists() and (not drv.exists() or drv.stat().st_mtime < src.stat().st_mtime):
-            return build_driver(ln)
-        return 0
-
-    OUT.mkdir(parents=True, exist_ok=True)
-    (BUILD / "obj").mkdir(parents=True, exist_ok=True)
+def prepare_lninclude() -> Path:
+    """The flat include directory (scratch, symlinks into the reference) + the one header fix."""
     ln = BUILD / "lnInclude"
     make_lninclude(ln, [REF / "src/OpenFOAM", REF / "src/OSspecific/POSIX"])
-
-    # -- scratch-copy fixes ---------------------------------------------------
     pbl = ln / "PackedBoolList.H"
     src = (REF / "src/OpenFOAM/containers/Lists/PackedList/PackedBoolList.H").read_text()
     src = src.replace("PackedBoolList& operator=(const UList<bool>&);",
@@ -129,6 +121,25 @@ def main():
     if pbl.is_symlink() or pbl.exists():
         pbl.unlink()
     pbl.write_text(src)
+    return ln
+
+
+def main():
+    if not REF.exists():
+        print(f"[build_ref] {REF} absent: using prebuilt oracle/_ref if any")
+        return 0 if (OUT / "libOpenFOAM.so").exists() else 1
+    if (OUT / "libOpenFOAM.so").exists() and "--force" not in sys.argv:
+        print("[build_ref] oracle/_ref/libOpenFOAM.so present (use --force to rebuild)")
+        srcs = [HERE / "ref_driver.C"] + sorted((HERE / "pstream_shm").glob("*"))
+        newest = max(p.stat().st_mtime for p in srcs)
+        outs = [OUT / "ref_driver", OUT / "ref_driver_par", OUT / "libPstream_shm.so"]
+        if all(o.exists() and o.stat().st_mtime >= newest for o in outs):
+            return 0
+        return build_driver(prepare_lninclude())
+
+    OUT.mkdir(parents=True, exist_ok=True)
+    (BUILD / "obj").mkdir(parents=True, exist_ok=True)
+    ln = prepare_lninclude()
 
     gver = (REF / "src/OpenFOAM/global/global.Cver").read_text()
     gver = gver.replace("VERSION_STRING", "2.2.x").replace("BUILD_STRING", "2.2.x-1f35a0ff")
@@ -192,6 +203,20 @@ def build_driver(ln: Path):
            f"-L{OUT} -lOpenFOAM -Wl,-rpath,$ORIGIN -ldl -lm")
     r = subprocess.run(cmd.split())
     print(f"[build_ref] ref_driver -> exit {r.returncode}")
+    if r.returncode:
+        return r.returncode
+    # the shared-memory Pstream and the multi-rank driver: same source, the seam listed first
+    shm = HERE / "pstream_shm"
+    cmd = (f"{CXX} {CXXFLAGS} -shared -I{shm} -I{ln} {shm / 'UPstream.C'} {shm / 'UIPread.C'} "
+           f"{shm / 'UOPwrite.C'} -o {OUT / 'libPstream_shm.so'}")
+    r = subprocess.run(cmd.split())
+    print(f"[build_ref] libPstream_shm.so -> exit {r.returncode}")
+    if r.returncode:
+        return r.returncode
+    cmd = (f"{CXX} {CXXFLAGS} -I{ln} {HERE / 'ref_driver.C'} -o {OUT / 'ref_driver_par'} "
+           f"-L{OUT} -Wl,--no-as-needed -lPstream_shm -lOpenFOAM -Wl,-rpath,$ORIGIN -ldl -lm")
+    r = subprocess.run(cmd.split())
+    print(f"[build_ref] ref_driver_par -> exit {r.returncode}")
     return r.returncode
 
 

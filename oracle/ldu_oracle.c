@@ -633,13 +633,51 @@ int orc_precondition(orc_world* w, int precond, double** wA, double** rA, int tr
  * (sym == 1).  Boundary: bPrime = source, then the interface update with
  * NEGATED bouCoeffs (GaussSeidelSmoother.C:110-145): bPrime[fc] -= (-bou)*psiNbr,
  * using psi of all regions from BEFORE this sweep (Jacobi coupling). */
-static void gs_sweeps(orc_matrix* ms, int R, double** psi, double** source, int nSweeps, int sym)
+static void gs_rows(const orc_matrix* m, double* x, double* bP, int c0, int c1)
+{
+    int c, f;
+    for (c = c0; c < c1; c++) {
+        int fs = m->ownerStart[c], fe = m->ownerStart[c + 1];
+        double psii = bP[c];
+        for (f = fs; f < fe; f++) psii -= m->upper[f] * x[m->u[f]];
+        psii /= m->diag[c];
+        for (f = fs; f < fe; f++) bP[m->u[f]] -= m->lower[f] * psii;
+        x[c] = psii;
+    }
+}
+
+/* nonBlocking == 1: nonBlockingGaussSeidelSmoother.C:66-81,128-217.  The cells below
+ * blockStart (the first cell on any interface) are swept BEFORE the interface update is
+ * consumed, so a coupled cell receives the lower-side contributions of those cells first,
+ * then the interface terms, then the rest: same operations as GaussSeidel, different
+ * rounding order on the coupled cells.  No interface cell changes in the first phase, so
+ * the neighbour values are still those from before the sweep. */
+static void gs_sweeps(orc_matrix* ms, int R, double** psi, double** source, int nSweeps, int sym,
+                      int nonBlocking)
 {
     double** bPrime = alloc_fields(ms, R);
-    int sweep, r, c, f;
+    int sweep, r, c, f, i, k;
     for (sweep = 0; sweep < nSweeps; sweep++) {
         for (r = 0; r < R; r++) {
             memcpy(bPrime[r], source[r], sizeof(double) * (size_t)ms[r].nCells);
+        }
+        if (nonBlocking) {
+            for (r = 0; r < R; r++) {
+                int blockStart = ms[r].nCells;
+                for (i = 0; i < ms[r].nIf; i++)
+                    for (k = 0; k < ms[r].ifs[i].n; k++)
+                        if (ms[r].ifs[i].faceCells[k] < blockStart) blockStart = ms[r].ifs[i].faceCells[k];
+                gs_rows(&ms[r], psi[r], bPrime[r], 0, blockStart);
+            }
+            for (r = 0; r < R; r++) update_interfaces(ms, R, r, bPrime[r], psi, 0, -1.0);
+            for (r = 0; r < R; r++) {
+                int blockStart = ms[r].nCells;
+                for (i = 0; i < ms[r].nIf; i++)
+                    for (k = 0; k < ms[r].ifs[i].n; k++)
+                        if (ms[r].ifs[i].faceCells[k] < blockStart) blockStart = ms[r].ifs[i].faceCells[k];
+                gs_rows(&ms[r], psi[r], bPrime[r], blockStart, ms[r].nCells);
+            }
+            continue;
         }
         for (r = 0; r < R; r++) update_interfaces(ms, R, r, bPrime[r], psi, 0, -1.0);
         /* all ranks sweep concurrently in the reference: interface values were
@@ -648,14 +686,7 @@ static void gs_sweeps(orc_matrix* ms, int R, double** psi, double** source, int 
             const orc_matrix* m = &ms[r];
             double* x = psi[r];
             double* bP = bPrime[r];
-            for (c = 0; c < m->nCells; c++) {
-                int fs = m->ownerStart[c], fe = m->ownerStart[c + 1];
-                double psii = bP[c];
-                for (f = fs; f < fe; f++) psii -= m->upper[f] * x[m->u[f]];
-                psii /= m->diag[c];
-                for (f = fs; f < fe; f++) bP[m->u[f]] -= m->lower[f] * psii;
-                x[c] = psii;
-            }
+            gs_rows(m, x, bP, 0, m->nCells);
             if (sym) {
                 for (c = m->nCells - 1; c >= 0; c--) {
                     int fs = m->ownerStart[c], fe = m->ownerStart[c + 1];
@@ -706,12 +737,13 @@ static int smooth_levels(orc_matrix* ms, int R, int smoother, double** psi, doub
 {
     switch (smoother) {
     case ORC_SMOOTHER_GS:
-    case ORC_SMOOTHER_NBGS: /* nonBlockingGaussSeidelSmoother.C:46-240: same
-                               arithmetic, cells reordered only in time */
-        gs_sweeps(ms, R, psi, source, nSweeps, 0);
+        gs_sweeps(ms, R, psi, source, nSweeps, 0, 0);
+        return 0;
+    case ORC_SMOOTHER_NBGS:
+        gs_sweeps(ms, R, psi, source, nSweeps, 0, 1);
         return 0;
     case ORC_SMOOTHER_SYMGS:
-        gs_sweeps(ms, R, psi, source, nSweeps, 1);
+        gs_sweeps(ms, R, psi, source, nSweeps, 1, 0);
         return 0;
     case ORC_SMOOTHER_DIC:
     case ORC_SMOOTHER_DILU:
@@ -720,11 +752,11 @@ static int smooth_levels(orc_matrix* ms, int R, int smoother, double** psi, doub
         return 0;
     case ORC_SMOOTHER_DICGS: /* DICGaussSeidelSmoother.C:79-89: DIC then GS, nSweeps each */
         dic_family_smooth(ms, R, psi, source, nSweeps, ORC_SMOOTHER_DIC);
-        gs_sweeps(ms, R, psi, source, nSweeps, 0);
+        gs_sweeps(ms, R, psi, source, nSweeps, 0, 0);
         return 0;
     case ORC_SMOOTHER_DILUGS:
         dic_family_smooth(ms, R, psi, source, nSweeps, ORC_SMOOTHER_DILU);
-        gs_sweeps(ms, R, psi, source, nSweeps, 0);
+        gs_sweeps(ms, R, psi, source, nSweeps, 0, 0);
         return 0;
     }
     return -1;

@@ -362,6 +362,86 @@ def ref_run(sysd, op, *args, psi=None, source=None, ints=False, timeout=3600):
     return out, r.stdout
 
 
+REF_DRIVER_PAR = HERE / "_ref" / "ref_driver_par"
+_SHM_WORLD_BYTES = 300 << 20     # >= sizeof(lduShm::World) (oracle/pstream_shm/shmWorld.H); sparse
+
+
+def ref_par_available() -> bool:
+    return REF_DRIVER_PAR.exists() and (HERE / "_ref" / "libPstream_shm.so").exists()
+
+
+def _write_region(path, reg, psi=None, source=None):
+    """'LDU2' problem file of one mesh region (oracle/ref_driver.C header)."""
+    asym = reg.get("lowerCoef") is not None
+    weights = reg.get("faceWeights") is not None
+    n = np.asarray(reg["diag"]).size
+    its = reg.get("interfaces", [])
+    with open(path, "wb") as fh:
+        np.array([0x3255444C, n, np.asarray(reg["lower"]).size, int(asym), int(weights), len(its)],
+                 dtype=np.int32).tofile(fh)
+        np.asarray(reg["lower"], dtype=np.int32).tofile(fh)
+        np.asarray(reg["upper"], dtype=np.int32).tofile(fh)
+        _f64(reg["diag"]).tofile(fh)
+        _f64(reg["upperCoef"]).tofile(fh)
+        if asym:
+            _f64(reg["lowerCoef"]).tofile(fh)
+        _f64(reg["source"] if source is None else source).tofile(fh)
+        _f64(np.zeros(n) if psi is None else psi).tofile(fh)
+        if weights:
+            _f64(reg["faceWeights"]).tofile(fh)
+        for it in its:
+            fc = np.asarray(it["faceCells"], dtype=np.int32)
+            np.array([it["nbrRegion"], fc.size], dtype=np.int32).tofile(fh)
+            fc.tofile(fh)
+            _f64(it["bouCoeffs"]).tofile(fh)
+            _f64(it["intCoeffs"]).tofile(fh)
+
+
+def ref_run_par(regions, op, *args, psi=None, source=None, ints=False, timeout=3600):
+    """Run the unmodified reference as one process per mesh region, coupled through
+    the shared-memory Pstream (oracle/pstream_shm).  psi/source: per-region lists.
+    Returns (list of per-region arrays, stdout of rank 0)."""
+    n = len(regions)
+    env = dict(os.environ, WM_PROJECT_DIR=str(HERE / "_ref"))
+    ld = env.get("LD_LIBRARY_PATH", "")
+    env["LD_LIBRARY_PATH"] = str(HERE / "_ref") + (":" + ld if ld else "")
+    shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory() as td, tempfile.NamedTemporaryFile(dir=shm_dir, prefix="ldu_pstream_") as seg:
+        seg.truncate(_SHM_WORLD_BYTES)
+        seg.flush()
+        for r, reg in enumerate(regions):
+            _write_region(os.path.join(td, f"p{r}.bin"), reg,
+                          psi=None if psi is None else psi[r], source=None if source is None else source[r])
+        procs = []
+        for r in range(n):
+            e = dict(env, LDU_PSTREAM_SHM=seg.name, LDU_PSTREAM_RANK=str(r), LDU_PSTREAM_SIZE=str(n))
+            procs.append(subprocess.Popen(
+                [str(REF_DRIVER_PAR), os.path.join(td, "p%d.bin"), os.path.join(td, "o%d.bin"), op,
+                 *[str(a) for a in args]],
+                env=e, stdout=subprocess.PIPE, stderr=None if os.environ.get("LDU_PSTREAM_STATS") else subprocess.PIPE, text=True, cwd=td))
+        outs = []
+        failed = None
+        for r, p in enumerate(procs):
+            try:
+                so, se = p.communicate(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            outs.append(so)
+            if p.returncode != 0 and failed is None:
+                failed = (r, p.returncode, so, se)
+                for q in procs:          # the others would wait for this rank for ever
+                    if q.poll() is None:
+                        q.kill()
+        if failed:
+            r, rc, so, se = failed
+            raise RuntimeError(f"ref_driver_par rank {r} failed ({rc}): {so[-2000:]}\n{se[-2000:]}")
+        res = [np.fromfile(os.path.join(td, f"o{r}.bin"), dtype=np.int32 if ints else np.float64)
+               for r in range(n)]
+    return res, outs[0]
+
+
 def parse_perf(stdout: str) -> dict:
     for line in stdout.splitlines():
         if line.startswith("PERF "):

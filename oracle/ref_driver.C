@@ -26,6 +26,17 @@
       f64   diag[nCells] upper[nFaces] (lower[nFaces] if asym)
       f64   source[nCells] psi0[nCells] (faceWeights[nFaces] if hasWeights)
 
+  Parallel mode (binary ref_driver_par, linked against oracle/_ref/libOpenFOAM_par.so =
+  the same objects with oracle/pstream_shm/ in place of src/Pstream/dummy): when
+  LDU_PSTREAM_SIZE is set, one process per mesh region is started; "%d" in the
+  problem / output paths is the rank, and the problem file (magic 'LDU2') carries
+  after the header one extra int32 nInterfaces and, at the end,
+      per interface: int32 nbrRank, int32 size, int32 faceCells[size],
+                     f64 bouCoeffs[size], f64 intCoeffs[size]
+  The interfaces are processor interfaces (classes below) doing what
+  processorFvPatch / processorFvPatchField<scalar> do in libfiniteVolume
+  (finiteVolume/fields/fvPatchFields/constraint/processor/processorFvPatchScalarField.C:33-116).
+
   Reference entry points exercised (all in /root/reference/src/OpenFOAM):
       lduMatrix::Amul/Tmul/sumA/residual   matrices/lduMatrix/lduMatrix/lduMatrixATmul.C:34-295
       lduMatrix::solver::New               matrices/lduMatrix/lduMatrix/lduMatrixSolver.C:40-136
@@ -43,6 +54,10 @@
 #include "pairGAMGAgglomeration.H"
 #include "addToRunTimeSelectionTable.H"
 #include "PCG.H"
+#include "processorLduInterface.H"
+#include "processorLduInterfaceField.H"
+#include "IPstream.H"
+#include "OPstream.H"
 
 #include <cstdio>
 #include <cstdlib>
@@ -121,6 +136,164 @@ addToRunTimeSelectionTable
 }
 
 
+
+// Processor interface of a flat LDU region: faceCells of the cut faces, the
+// neighbouring rank, raw transfers through processorLduInterface::send/receive.
+// Type name "processor" so that GAMGInterface::New / GAMGInterfaceField::New
+// select processorGAMGInterface(Field) on the coarse levels
+// (GAMGInterface/GAMGInterfaceNew.C:32-62, GAMGInterfaceField/GAMGInterfaceFieldNew.C:31-56).
+namespace Foam
+{
+class flatProcessorInterface
+:
+    public lduInterface,
+    public processorLduInterface
+{
+    labelList faceCells_;
+    int nbr_;
+    tensorField noTransform_;
+
+public:
+    TypeName("processor");
+
+    flatProcessorInterface(const labelList& fc, const int nbr)
+    :
+        faceCells_(fc),
+        nbr_(nbr),
+        noTransform_(0)
+    {}
+
+    virtual const labelUList& faceCells() const { return faceCells_; }
+    virtual int myProcNo() const { return Pstream::myProcNo(); }
+    virtual int neighbProcNo() const { return nbr_; }
+    virtual const tensorField& forwardT() const { return noTransform_; }
+    virtual int tag() const { return Pstream::msgType(); }
+
+    virtual tmp<labelField> interfaceInternalField(const labelUList& iF) const
+    {
+        tmp<labelField> tf(new labelField(faceCells_.size()));
+        labelField& pf = tf();
+        forAll(pf, i) pf[i] = iF[faceCells_[i]];
+        return tf;
+    }
+
+    virtual void initInternalFieldTransfer
+    (
+        const Pstream::commsTypes commsType,
+        const labelUList& iF
+    ) const
+    {
+        send(commsType, interfaceInternalField(iF)());
+    }
+
+    virtual tmp<labelField> internalFieldTransfer
+    (
+        const Pstream::commsTypes commsType,
+        const labelUList&
+    ) const
+    {
+        return receive<label>(commsType, faceCells_.size());
+    }
+};
+
+defineTypeNameAndDebug(flatProcessorInterface, 0);
+
+
+class flatProcessorInterfaceField
+:
+    public lduInterfaceField,
+    public processorLduInterfaceField
+{
+    const flatProcessorInterface& patch_;
+    mutable scalarField sendBuf_;
+    mutable scalarField recvBuf_;
+    mutable label recvRequest_;
+
+public:
+    TypeName("processor");
+
+    flatProcessorInterfaceField(const flatProcessorInterface& p)
+    :
+        lduInterfaceField(p),
+        patch_(p),
+        recvRequest_(-1)
+    {}
+
+    virtual int myProcNo() const { return patch_.myProcNo(); }
+    virtual int neighbProcNo() const { return patch_.neighbProcNo(); }
+    virtual bool doTransform() const { return false; }
+    virtual const tensorField& forwardT() const { return patch_.forwardT(); }
+    virtual int rank() const { return 0; }
+
+    // psi next to the cut goes to the neighbour ...
+    virtual void initInterfaceMatrixUpdate
+    (
+        scalarField&,
+        const scalarField& psiInternal,
+        const scalarField&,
+        const direction,
+        const Pstream::commsTypes commsType
+    ) const
+    {
+        const labelUList& fc = patch_.faceCells();
+        sendBuf_.setSize(fc.size());
+        forAll(fc, i) sendBuf_[i] = psiInternal[fc[i]];
+
+        if (commsType == Pstream::nonBlocking)
+        {
+            recvBuf_.setSize(fc.size());
+            recvRequest_ = UPstream::nRequests();
+            IPstream::read
+            (
+                commsType, patch_.neighbProcNo(),
+                reinterpret_cast<char*>(recvBuf_.begin()), recvBuf_.byteSize(), patch_.tag()
+            );
+            OPstream::write
+            (
+                commsType, patch_.neighbProcNo(),
+                reinterpret_cast<const char*>(sendBuf_.begin()), sendBuf_.byteSize(), patch_.tag()
+            );
+        }
+        else
+        {
+            patch_.send(commsType, sendBuf_);
+        }
+        const_cast<flatProcessorInterfaceField&>(*this).updatedMatrix() = false;
+    }
+
+    // ... and the neighbour's values come back: result[faceCell] -= coeff*psiNbr
+    virtual void updateInterfaceMatrix
+    (
+        scalarField& result,
+        const scalarField&,
+        const scalarField& coeffs,
+        const direction,
+        const Pstream::commsTypes commsType
+    ) const
+    {
+        if (updatedMatrix()) return;
+        const labelUList& fc = patch_.faceCells();
+        if (commsType == Pstream::nonBlocking)
+        {
+            if (recvRequest_ >= 0 && recvRequest_ < UPstream::nRequests())
+            {
+                UPstream::waitRequest(recvRequest_);
+            }
+            recvRequest_ = -1;
+        }
+        else
+        {
+            recvBuf_.setSize(fc.size());
+            patch_.receive(commsType, recvBuf_);
+        }
+        forAll(fc, i) result[fc[i]] -= coeffs[i]*recvBuf_[i];
+        const_cast<flatProcessorInterfaceField&>(*this).updatedMatrix() = true;
+    }
+};
+
+defineTypeNameAndDebug(flatProcessorInterfaceField, 0);
+}
+
 static dictionary dictFromText(const std::string& text)
 {
     IStringStream is(text);
@@ -160,15 +333,26 @@ int main(int argc, char* argv[])
         fprintf(stderr, "usage: ref_driver problem out op [args]\n");
         return 2;
     }
-    const char* probFile = argv[1];
-    const char* outFile = argv[2];
+    const bool parallel = getenv("LDU_PSTREAM_SIZE") != NULL;
+    if (parallel)
+    {
+        UPstream::init(argc, argv);     // oracle/pstream_shm/UPstream.C
+    }
+    char probFile[4096], outFile[4096];
+    snprintf(probFile, sizeof(probFile), argv[1], int(Pstream::myProcNo()));
+    snprintf(outFile, sizeof(outFile), argv[2], int(Pstream::myProcNo()));
     const std::string op(argv[3]);
 
     FILE* f = fopen(probFile, "rb");
     if (!f) { perror(probFile); return 2; }
     int hdr[5];
     readOrDie(hdr, sizeof(int), 5, f);
-    if (hdr[0] != 0x3155444c) { fprintf(stderr, "bad magic\n"); return 2; }
+    int nInterfaces = 0;
+    if (hdr[0] == 0x3255444c)           // 'LDU2': processor interfaces follow the fields
+    {
+        readOrDie(&nInterfaces, sizeof(int), 1, f);
+    }
+    else if (hdr[0] != 0x3155444c) { fprintf(stderr, "bad magic\n"); return 2; }
     const label nCells = hdr[1];
     const label nFaces = hdr[2];
     const bool asym = hdr[3];
@@ -191,13 +375,36 @@ int main(int argc, char* argv[])
         readOrDie(faceWeights.begin(), sizeof(scalar), nFaces, f);
         gFaceWeights = &faceWeights;
     }
+    PtrList<flatProcessorInterface> procPatches(nInterfaces);
+    PtrList<flatProcessorInterfaceField> procFields(nInterfaces);
+    labelListList patchAddr(nInterfaces);
+    lduInterfacePtrsList meshInterfaces(nInterfaces);
+    lduSchedule schedule(2*nInterfaces);
+    FieldField<Field, scalar> bouCoeffs(nInterfaces);
+    FieldField<Field, scalar> intCoeffs(nInterfaces);
+    lduInterfaceFieldPtrsList interfaces(nInterfaces);
+    for (int i = 0; i < nInterfaces; i++)
+    {
+        int ih[2];
+        readOrDie(ih, sizeof(int), 2, f);
+        patchAddr[i].setSize(ih[1]);
+        readOrDie(patchAddr[i].begin(), sizeof(label), ih[1], f);
+        bouCoeffs.set(i, new scalarField(ih[1]));
+        intCoeffs.set(i, new scalarField(ih[1]));
+        readOrDie(bouCoeffs[i].begin(), sizeof(scalar), ih[1], f);
+        readOrDie(intCoeffs[i].begin(), sizeof(scalar), ih[1], f);
+        procPatches.set(i, new flatProcessorInterface(patchAddr[i], ih[0]));
+        procFields.set(i, new flatProcessorInterfaceField(procPatches[i]));
+        meshInterfaces.set(i, &procPatches[i]);
+        interfaces.set(i, &procFields[i]);
+        schedule[2*i].patch = i;
+        schedule[2*i].init = true;
+        schedule[2*i + 1].patch = i;
+        schedule[2*i + 1].init = false;
+    }
     fclose(f);
 
     Time runTime(fileName("."), fileName("."));
-
-    labelListList patchAddr(0);
-    lduInterfacePtrsList meshInterfaces(0);
-    lduSchedule schedule(0);
 
     registryLduMesh mesh
     (
@@ -208,10 +415,6 @@ int main(int argc, char* argv[])
     A.diag() = diag;
     A.upper() = upper;
     if (asym) A.lower() = lower;
-
-    FieldField<Field, scalar> bouCoeffs(0);
-    FieldField<Field, scalar> intCoeffs(0);
-    lduInterfaceFieldPtrsList interfaces(0);
 
     scalarField out(nCells, 0.0);
     std::vector<int> outInts;

@@ -1,5 +1,7 @@
 """Shared case tables: the systems and solver dictionaries the oracle is pinned on
 (against the compiled reference and the golden fixtures) and the GPU is checked on."""
+import numpy as np
+
 from ldub200 import meshes
 
 SYSTEMS = {
@@ -79,6 +81,50 @@ GAMG_SOLVES = [
                                            mergeLevels=1, cacheAgglomeration=False, tolerance=1e-5,
                                            relTol=0, nVcycles=2))),
 ]
+
+# (system, regions, partition, controls): the system cut into one mesh region per rank
+# (ldub200.decompose), solved by the coupled reference (one process per region) / the oracle
+# World / the multi-GPU path
+MULTI_REGION_SOLVES = [
+    ("box6x40x9", 2, "slab", dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)),
+    ("box6x40x9", 4, "slab", dict(solver="PCG", preconditioner="FDIC", tolerance=1e-8, relTol=0)),
+    ("box6x40x9", 3, "random", dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)),
+    ("cavity20x20", 2, "slab", dict(solver="PCG", preconditioner="diagonal", tolerance=1e-6, relTol=0)),
+    ("asym4x35x13", 4, "slab", dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)),
+    ("asym10", 2, "random", dict(solver="PBiCG", preconditioner="diagonal", tolerance=1e-8, relTol=0)),
+    ("asym4x35x13", 2, "slab", dict(solver="smoothSolver", smoother="GaussSeidel", nSweeps=2, tolerance=1e-6,
+                                     relTol=0, maxIter=50)),
+    ("box6x40x9", 2, "slab", dict(solver="smoothSolver", smoother="DICGaussSeidel", nSweeps=1, tolerance=1e-6,
+                                   relTol=0, maxIter=50)),
+    ("box12_var", 3, "slab", dict(solver="smoothSolver", smoother="symGaussSeidel", nSweeps=2, tolerance=1e-6,
+                                   relTol=0, maxIter=40)),
+    ("box12_var", 2, "slab", dict(solver="smoothSolver", smoother="nonBlockingGaussSeidel", nSweeps=2,
+                                   tolerance=1e-6, relTol=0, maxIter=40)),
+    ("box6x40x9", 2, "slab", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0)),
+    ("box12_var", 4, "slab", dict(_GAMG, agglomerator="faceAreaPair", mergeLevels=2, tolerance=1e-8, relTol=0)),
+    ("box40x30x20", 4, "slab", dict(_GAMG, agglomerator="algebraicPair", tolerance=1e-8, relTol=0)),
+    ("asym33x17x11", 4, "slab", dict(_GAMG, smoother="DILU", agglomerator="faceAreaPair", tolerance=1e-8,
+                                      relTol=0)),
+    ("box12_var", 2, "random", dict(solver="PCG", tolerance=1e-9, relTol=0,
+                                     preconditioner=dict(preconditioner="GAMG", smoother="GaussSeidel",
+                                                         agglomerator="faceAreaPair", nCellsInCoarsestLevel=10,
+                                                         mergeLevels=1, cacheAgglomeration=False, tolerance=1e-5,
+                                                         relTol=0, nVcycles=2))),
+]
+
+
+def regions(name, n_regions, partition):
+    """system `name` cut into n_regions mesh regions: contiguous cell ranges ("slab") or a
+    seeded random cell -> region map ("random": every region touches every other one)."""
+    from ldub200 import decompose
+    s = system(name)
+    n = s["nCells"]
+    if partition == "slab":
+        proc = (np.arange(n) * n_regions // n).astype(np.int32)
+    else:
+        proc = np.random.default_rng(n_regions).integers(0, n_regions, n).astype(np.int32)
+    return s, decompose.decompose(s, proc, n_regions)
+
 
 PRECONDITIONERS = ["none", "diagonal", "DIC", "FDIC", "DILU"]
 SMOOTHERS = ["GaussSeidel", "symGaussSeidel", "DIC", "DILU", "FDIC", "DICGaussSeidel",

@@ -62,6 +62,34 @@ def main():
             agg[f"{name}_m{merge}_l{lev}"] = L["restrict"].astype(np.int32)
     np.savez_compressed(HERE / "agglomeration.npz", **agg)
     print("agglomeration", len(agg))
+    # multi-region: the reference as one process per region over the shared-memory Pstream
+    # (oracle/pstream_shm); fields stored gathered into the global cell order
+    assert O.ref_par_available(), "oracle/_ref/ref_driver_par missing"
+    from ldub200 import decompose
+    multi = {}
+    for i, (name, R, part, ctl) in enumerate(cases.MULTI_REGION_SOLVES):
+        s, regs = cases.regions(name, R, part)
+        psi, so = O.ref_run_par(regs, "solve", O.dict_text(cases.ref_controls(ctl)))
+        perf = O.parse_perf(so)
+        multi[f"psi_{i}"] = decompose.gather_field(regs, psi, s["nCells"])
+        multi[f"perf_{i}"] = np.array([perf["initialResidual"], perf["finalResidual"],
+                                       perf["nIterations"], perf["converged"], perf["singular"]], dtype=np.float64)
+        print("multi-region solve", i, name, R, part, ctl["solver"], perf["nIterations"])
+    for name, R, part in [("asym4x35x13", 4, "slab"), ("box12_var", 3, "random")]:
+        s, regs = cases.regions(name, R, part)
+        x = rng.standard_normal(s["nCells"])
+        xs = [x[r["cells"]] for r in regs]
+        key = f"{name}_{R}_{part}"
+        multi[key + "_x"] = x
+        for op in ("amul", "tmul", "suma", "residual"):
+            out = O.ref_run_par(regs, op, psi=xs)[0]
+            multi[f"{key}_{op}"] = decompose.gather_field(regs, out, s["nCells"])
+        for sm in cases.SMOOTHERS:
+            if cases.selectable(s, sm):
+                out = O.ref_run_par(regs, "smooth", O.dict_text(dict(smoother=sm)), 2, psi=xs)[0]
+                multi[f"{key}_smooth_{sm}"] = decompose.gather_field(regs, out, s["nCells"])
+    np.savez_compressed(HERE / "multi_region.npz", **multi)
+    print("multi-region", len(multi))
 
 
 if __name__ == "__main__":

@@ -76,3 +76,47 @@ def test_do_while_off_by_one():
                                    nCellsInCoarsestLevel=10, mergeLevels=1, tolerance=0, relTol=0, maxIter=3),
                               s["psi0"], s["source"])
     assert p["nIterations"] == 3
+
+
+# --- multi-region: outputs of the reference run as one process per region (coupled through
+# --- oracle/pstream_shm), stored gathered into the global cell order
+@pytest.mark.parametrize("case", range(len(cases.MULTI_REGION_SOLVES)))
+def test_multi_region_solves(case):
+    from ldub200 import decompose
+    g = np.load(GOLD / "multi_region.npz")
+    name, R, part, ctl = cases.MULTI_REGION_SOLVES[case]
+    s, regs = cases.regions(name, R, part)
+    psi, perf = O.World(regs).solve(ctl, [r["psi0"] for r in regs], [r["source"] for r in regs])
+    ref = g[f"perf_{case}"]
+    assert perf["initialResidual"] == ref[0]
+    assert perf["finalResidual"] == ref[1]
+    assert perf["nIterations"] == int(ref[2])
+    assert perf["converged"] == bool(ref[3]) and perf["singular"] == bool(ref[4])
+    assert np.array_equal(decompose.gather_field(regs, psi, s["nCells"]), g[f"psi_{case}"])
+
+
+@pytest.mark.parametrize("name,R,part", [("asym4x35x13", 4, "slab"), ("box12_var", 3, "random")])
+def test_multi_region_operators_and_smoothers(name, R, part):
+    from ldub200 import decompose
+    g = np.load(GOLD / "multi_region.npz")
+    s, regs = cases.regions(name, R, part)
+    key = f"{name}_{R}_{part}"
+    x = g[key + "_x"]
+    xs = [x[r["cells"]] for r in regs]
+    src = [r["source"] for r in regs]
+    w = O.World(regs)
+
+    def gathered(fields):
+        return decompose.gather_field(regs, fields, s["nCells"])
+
+    assert np.array_equal(gathered(w.amul(xs)), g[key + "_amul"])
+    assert np.array_equal(gathered(w.tmul(xs)), g[key + "_tmul"])
+    assert np.array_equal(gathered(w.sumA()), g[key + "_suma"])
+    assert np.array_equal(gathered(w.residual(xs, src)), g[key + "_residual"])
+    checked = 0
+    for k in g.files:
+        if k.startswith(key + "_smooth_"):
+            sm = k[len(key) + 8:]
+            assert np.array_equal(gathered(w.smooth(sm, xs, src, 2)), g[k]), sm
+            checked += 1
+    assert checked >= 5
