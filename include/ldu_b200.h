@@ -104,6 +104,9 @@ const char* ldu_last_error(void);
 /* number of CUDA kernels this library has launched in this process */
 long long ldu_launch_count(void);
 
+/* CUDA devices visible to this process (0 when there is none); a multi-rank host binds rank r to
+ * device r % count, the way mpirun-launched applications pick a GPU per rank */
+int ldu_device_count(void);
 /* device: CUDA ordinal; stream: a cudaStream_t to enqueue on (NULL = create one) */
 int ldu_context_create(int device, void* stream, ldu_context** out);
 int ldu_context_destroy(ldu_context* ctx);

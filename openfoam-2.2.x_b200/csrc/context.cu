@@ -94,6 +94,13 @@ void ldu_controls_default(ldu_controls* c)
     c->checkInterval = 0;
 }
 
+int ldu_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
 int ldu_context_create(int device, void* stream, ldu_context** out)
 {
     if (!out) return LDU_EINVAL;

@@ -5,6 +5,10 @@
 #include "gpuLduSolvers.H"
 #include "addToRunTimeSelectionTable.H"
 #include "Switch.H"
+#include "processorLduInterface.H"
+#include "PstreamReduceOps.H"
+#include "UIPstream.H"
+#include "UOPstream.H"
 
 #include "../../include/ldu_b200.h"
 
@@ -97,15 +101,123 @@ void check(const int rc, const char* what)
     }
 }
 
+// One context per process; in a parallel run rank r takes device r % nDevices
+// (LDU_DEVICE overrides), the usual one-rank-per-GPU binding.
 ldu_context* context()
 {
     static ldu_context* ctx = NULL;
     if (!ctx)
     {
         const char* e = ::getenv("LDU_DEVICE");
-        check(ldu_context_create(e ? ::atoi(e) : 0, NULL, &ctx), "ldu_context_create");
+        int device = e ? ::atoi(e) : 0;
+        if (!e && Pstream::parRun())
+        {
+            const int n = ldu_device_count();
+            device = n > 0 ? Pstream::myProcNo() % n : 0;
+        }
+        check(ldu_context_create(device, NULL, &ctx), "ldu_context_create");
     }
     return ctx;
+}
+
+// The coupled patches of a matrix as the C ABI wants them.  Processor patches only:
+// the other side lives on another rank (another GPU), faces in the same order on
+// both sides (processorLduInterface.H:88-97).
+struct coupledPatches
+{
+    DynamicList<label> patchIDs;      // interfaces_ index of compact interface i
+    DynamicList<int> sizes;
+    DynamicList<int> nbrRank;
+    DynamicList<const int*> faceCells;
+};
+
+void findCoupledPatches
+(
+    const lduMatrix& A,
+    const lduInterfaceFieldPtrsList& interfaces,
+    coupledPatches& cp
+)
+{
+    forAll(interfaces, patchi)
+    {
+        if (!interfaces.set(patchi)) continue;
+        const lduInterface& li = interfaces[patchi].interface();
+        if (!isA<processorLduInterface>(li))
+        {
+            FatalErrorIn("gpuLduSolver::solve")
+                << "coupled patch " << patchi << " of type " << li.type()
+                << ": only processor patches are handed to the GPU solver"
+                   " (cyclic patches: not yet)" << exit(FatalError);
+        }
+        const labelUList& fc = A.lduAddr().patchAddr(patchi);
+        cp.patchIDs.append(patchi);
+        cp.sizes.append(fc.size());
+        cp.nbrRank.append(refCast<const processorLduInterface>(li).neighbProcNo());
+        cp.faceCells.append(fc.begin());
+    }
+}
+
+// Exchange window between the GPUs of a parallel run (ldu_b200.h: ldu_comm_*): the
+// 64-byte handles travel once over the application's own Pstream, after that halos
+// and sums go GPU to GPU.  Collective: every rank gets here in its first coupled solve.
+void connectDevices(const coupledPatches& cp)
+{
+    static bool connected = false;
+    static label windowInterfaces = 0, windowFaces = 0;
+    label nIfs = cp.sizes.size(), nFaces = 1;
+    forAll(cp.sizes, i) nFaces = max(nFaces, label(cp.sizes[i]));
+    if (connected)
+    {
+        if (nIfs > windowInterfaces || nFaces > windowFaces)
+        {
+            FatalErrorIn("gpuLduSolver::solve")
+                << "matrix with more/larger coupled patches than the exchange window"
+                   " was created for" << exit(FatalError);
+        }
+        return;
+    }
+    reduce(nIfs, maxOp<label>());
+    reduce(nFaces, maxOp<label>());
+    const label me = Pstream::myProcNo(), n = Pstream::nProcs();
+    List<char> all(n*LDU_COMM_HANDLE_BYTES);
+    unsigned char* mine = reinterpret_cast<unsigned char*>(&all[me*LDU_COMM_HANDLE_BYTES]);
+    check
+    (
+        ldu_comm_window_create(context(), me, n, nIfs, nFaces, mine),
+        "ldu_comm_window_create"
+    );
+    for (label proc = 0; proc < n; proc++)
+    {
+        if (proc != me)
+        {
+            UOPstream::write
+            (
+                Pstream::blocking, proc,
+                reinterpret_cast<const char*>(mine), LDU_COMM_HANDLE_BYTES
+            );
+        }
+    }
+    for (label proc = 0; proc < n; proc++)
+    {
+        if (proc != me)
+        {
+            UIPstream::read
+            (
+                Pstream::blocking, proc,
+                &all[proc*LDU_COMM_HANDLE_BYTES], LDU_COMM_HANDLE_BYTES
+            );
+        }
+    }
+    check
+    (
+        ldu_comm_connect(context(), reinterpret_cast<const unsigned char*>(all.begin())),
+        "ldu_comm_connect"
+    );
+    label sync = 0;
+    reduce(sync, sumOp<label>());    // nobody starts before every window is mapped
+    windowInterfaces = nIfs;
+    windowFaces = nFaces;
+    connected = true;
 }
 
 // Device copy of the addressing, built once per lduAddressing and kept for the
@@ -118,7 +230,7 @@ struct cachedMatrix
     label nFaces;
 };
 
-ldu_matrix* deviceMatrix(const lduMatrix& A)
+ldu_matrix* deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
 {
     static std::map<const lduAddressing*, cachedMatrix> cache;
     const lduAddressing& addr = A.lduAddr();
@@ -136,6 +248,31 @@ ldu_matrix* deviceMatrix(const lduMatrix& A)
         cache.erase(it);
     }
 
+    // index of the matching interface in the neighbour's (compact) list: each side
+    // tells the other (patches towards one neighbour are in the same order on both sides)
+    List<int> nbrInterface(cp.sizes.size(), 0);
+    if (cp.sizes.size())
+    {
+        connectDevices(cp);
+        forAll(nbrInterface, i)
+        {
+            const int mine = i;
+            UOPstream::write
+            (
+                Pstream::blocking, cp.nbrRank[i],
+                reinterpret_cast<const char*>(&mine), sizeof(int)
+            );
+        }
+        forAll(nbrInterface, i)
+        {
+            UIPstream::read
+            (
+                Pstream::blocking, cp.nbrRank[i],
+                reinterpret_cast<char*>(&nbrInterface[i]), sizeof(int)
+            );
+        }
+    }
+
     cachedMatrix c;
     c.nCells = nCells;
     c.nFaces = nFaces;
@@ -146,7 +283,12 @@ ldu_matrix* deviceMatrix(const lduMatrix& A)
         (
             context(), nCells, nFaces,
             addr.lowerAddr().begin(), addr.upperAddr().begin(),
-            0, NULL, NULL, NULL, NULL, &c.m
+            cp.sizes.size(),
+            cp.sizes.size() ? cp.sizes.begin() : NULL,
+            cp.sizes.size() ? cp.faceCells.begin() : NULL,
+            cp.sizes.size() ? cp.nbrRank.begin() : NULL,
+            cp.sizes.size() ? nbrInterface.begin() : NULL,
+            &c.m
         ),
         "ldu_matrix_create"
     );
@@ -283,19 +425,17 @@ Foam::solverPerformance Foam::gpuLduSolver::solve
     const direction
 ) const
 {
-    forAll(interfaces_, patchi)
-    {
-        if (interfaces_.set(patchi))
-        {
-            FatalErrorIn("gpuLduSolver::solve")
-                << "coupled patches (processor/cyclic) reach the GPU solver through"
-                   " ldu_matrix_create's interface arguments, which this shim does"
-                   " not fill yet; run the case undecomposed"
-                << exit(FatalError);
-        }
-    }
+    coupledPatches cp;
+    findCoupledPatches(matrix_, interfaces_, cp);
+    ldu_matrix* m = deviceMatrix(matrix_, cp);
 
-    ldu_matrix* m = deviceMatrix(matrix_);
+    // interfaceBouCoeffs_/interfaceIntCoeffs_ of the coupled patches (lduMatrix.H:97-104)
+    List<const double*> bou(cp.patchIDs.size()), intc(cp.patchIDs.size());
+    forAll(cp.patchIDs, i)
+    {
+        bou[i] = interfaceBouCoeffs_[cp.patchIDs[i]].begin();
+        intc[i] = interfaceIntCoeffs_[cp.patchIDs[i]].begin();
+    }
 
     check
     (
@@ -305,8 +445,8 @@ Foam::solverPerformance Foam::gpuLduSolver::solve
             matrix_.diag().begin(),
             matrix_.upper().begin(),
             matrix_.asymmetric() ? matrix_.lower().begin() : NULL,
-            NULL,
-            NULL
+            bou.size() ? bou.begin() : NULL,
+            intc.size() ? intc.begin() : NULL
         ),
         "ldu_matrix_set_coeffs"
     );

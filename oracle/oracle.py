@@ -397,12 +397,12 @@ def _write_region(path, reg, psi=None, source=None):
             _f64(it["intCoeffs"]).tofile(fh)
 
 
-def ref_run_par(regions, op, *args, psi=None, source=None, ints=False, timeout=3600):
+def ref_run_par(regions, op, *args, psi=None, source=None, ints=False, timeout=3600, extra_env=None):
     """Run the unmodified reference as one process per mesh region, coupled through
     the shared-memory Pstream (oracle/pstream_shm).  psi/source: per-region lists.
     Returns (list of per-region arrays, stdout of rank 0)."""
     n = len(regions)
-    env = dict(os.environ, WM_PROJECT_DIR=str(HERE / "_ref"))
+    env = dict(os.environ, WM_PROJECT_DIR=str(HERE / "_ref"), **(extra_env or {}))
     ld = env.get("LD_LIBRARY_PATH", "")
     env["LD_LIBRARY_PATH"] = str(HERE / "_ref") + (":" + ld if ld else "")
     shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else None

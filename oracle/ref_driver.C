@@ -19,6 +19,8 @@
                                                   nFine, nCoarse, restrict[nFine]
       time_amul <reps>                         -> TIME line (seconds per Amul)
       time_solve "<dict text>"                 -> TIME + PERF lines
+  Environment: LDU_REF_LIBS=<lib.so> is opened through the Time's dlLibraryTable before the
+  operation (the `libs` entry of a case's controlDict), so a dictionary may select a plug-in.
 
   Problem file (little endian):
       int32 magic(0x3155444c 'LDU1') nCells nFaces asym hasWeights
@@ -58,6 +60,7 @@
 #include "processorLduInterfaceField.H"
 #include "IPstream.H"
 #include "OPstream.H"
+#include "dlLibraryTable.H"
 
 #include <cstdio>
 #include <cstdlib>
@@ -405,6 +408,18 @@ int main(int argc, char* argv[])
     fclose(f);
 
     Time runTime(fileName("."), fileName("."));
+
+    // LDU_REF_LIBS=<lib.so>: what `libs ("lib.so");` in system/controlDict does (Time.C:343 ->
+    // dlLibraryTable::open): the solver dictionary can then name run-time selected plug-ins
+    if (getenv("LDU_REF_LIBS"))
+    {
+        dictionary libsDict(dictFromText(std::string("libs (\"") + getenv("LDU_REF_LIBS") + "\");"));
+        if (!runTime.libs().open(libsDict, "libs"))
+        {
+            fprintf(stderr, "ref_driver: could not load %s\n", getenv("LDU_REF_LIBS"));
+            return 3;
+        }
+    }
 
     registryLduMesh mesh
     (

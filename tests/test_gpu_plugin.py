@@ -69,3 +69,43 @@ def test_override_mode_replaces_reference_names(tmp_path):
     ctl = dict(solver="PCG", preconditioner="DIC", tolerance=1e-6, relTol=0)
     r = run_driver("cavity20x20", ctl, tmp_path, override=True)
     assert r["it_ref"] == r["it_gpu"]
+
+
+# --- multi-rank: the reference's host program as one process per mesh region (coupled through
+# --- the shared-memory Pstream, oracle/pstream_shm), every rank solving through the plug-in on a
+# --- GPU; processor patches become the library's interfaces, halos and sums go GPU to GPU
+def run_par(regs, controls, plugin):
+    if not (PLUGIN.exists() and O.ref_par_available()):
+        pytest.skip("plug-in / parallel reference driver not built (need /root/reference at build time)")
+    env = dict(LDU_REF_LIBS=str(PLUGIN)) if plugin else None
+    psi, so = O.ref_run_par(regs, "solve", O.dict_text(cases.ref_controls(controls)), extra_env=env, timeout=300)
+    return psi, O.parse_perf(so)
+
+
+@pytest.mark.parametrize("name,R,part,controls", [
+    ("box12_var", 2, "slab", dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)),
+    ("box6x40x9", 4, "slab", dict(solver="PCG", preconditioner="FDIC", tolerance=1e-8, relTol=0)),
+    ("asym4x35x13", 3, "random", dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)),
+    ("box12_var", 2, "slab", dict(solver="smoothSolver", smoother="nonBlockingGaussSeidel", nSweeps=2,
+                                   tolerance=1e-6, relTol=0, maxIter=40)),
+    ("box40x30x20", 4, "slab", dict(solver="GAMG", smoother="GaussSeidel", agglomerator="algebraicPair",
+                                     nCellsInCoarsestLevel=10, mergeLevels=1, cacheAgglomeration=False,
+                                     tolerance=1e-8, relTol=0)),
+])
+def test_plugin_multi_rank_bit_identical(name, R, part, controls):
+    import numpy as np
+    s, regs = cases.regions(name, R, part)
+    gpu = {"PCG": "gpuPCG", "PBiCG": "gpuPBiCG", "smoothSolver": "gpuSmoothSolver", "GAMG": "gpuGAMG"}
+    psi_ref, perf_ref = run_par(regs, controls, plugin=False)
+    psi_gpu, perf_gpu = run_par(regs, dict(controls, solver=gpu[controls["solver"]], referenceOrderSums=True),
+                                plugin=True)
+    assert perf_gpu["solverName"] == perf_ref["solverName"]
+    assert perf_gpu["nIterations"] == perf_ref["nIterations"]
+    assert perf_gpu["initialResidual"] == perf_ref["initialResidual"]
+    assert perf_gpu["finalResidual"] == perf_ref["finalResidual"]
+    for a, b in zip(psi_gpu, psi_ref):
+        assert np.array_equal(a, b)
+    # default (tree-ordered) sums: same iteration count, residual equal to rounding
+    psi_fast, perf_fast = run_par(regs, dict(controls, solver=gpu[controls["solver"]]), plugin=True)
+    assert perf_fast["nIterations"] == perf_ref["nIterations"]
+    assert abs(perf_fast["finalResidual"] - perf_ref["finalResidual"]) <= 1e-4 * perf_ref["finalResidual"] + 1e-13
