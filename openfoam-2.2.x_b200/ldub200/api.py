@@ -43,7 +43,7 @@ _lib = None
 
 # every symbol include/ldu_b200.h declares (tests check the .so exports them all)
 ABI_SYMBOLS = [
-    "ldu_version", "ldu_last_error", "ldu_launch_count", "ldu_context_create", "ldu_context_destroy",
+    "ldu_version", "ldu_last_error", "ldu_launch_count", "ldu_device_count", "ldu_context_create", "ldu_context_destroy",
     "ldu_context_synchronize", "ldu_context_stream", "ldu_comm_window_create", "ldu_comm_connect",
     "ldu_device_alloc", "ldu_device_free", "ldu_copy_h2d", "ldu_copy_d2h", "ldu_device_memset", "ldu_host_alloc",
     "ldu_host_free", "ldu_matrix_create", "ldu_matrix_destroy", "ldu_matrix_set_coeffs",
@@ -123,6 +123,11 @@ def _check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(library().ldu_launch_count())
+
+
+def device_count() -> int:
+    """CUDA devices visible to this process (rank r of a parallel run binds r % device_count())."""
+    return int(library().ldu_device_count())
 
 
 def make_controls(d: dict) -> Controls:
