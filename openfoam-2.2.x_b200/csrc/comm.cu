@@ -114,12 +114,33 @@ static int ensure_iface_table(ldu_matrix* m, IfaceDev** out)
 static int halo_grid(ldu_matrix* m, dim3& grid, IfaceDev** tab)
 {
     ldu_context* ctx = m->ctx;
-    if (!ctx->comm.connected) {
-        set_error("matrix has coupled interfaces but the context has no peers (ldu_comm_connect)");
-        return LDU_ECOMM;
-    }
     int maxN = 0;
-    for (const Interface& it : m->ifs) maxN = std::max(maxN, it.n);
+    bool allSelf = true;
+    for (const Interface& it : m->ifs) {
+        maxN = std::max(maxN, it.n);
+        allSelf = allSelf && it.nbrRank == 0;
+    }
+    if (!ctx->comm.connected || (ctx->comm.selfOnly && allSelf
+                                 && ((int)m->ifs.size() > ctx->comm.maxInterfaces || maxN > ctx->comm.slotStride))) {
+        // a single process whose coupled patches all point back into the region itself (cyclic
+        // pairs): it is its own only peer, the window is made (or re-made larger) on demand
+        if (!allSelf || (ctx->comm.connected && !ctx->comm.selfOnly)) {
+            set_error("matrix has coupled interfaces but the context has no peers (ldu_comm_connect)");
+            return LDU_ECOMM;
+        }
+        if (ctx->comm.connected) {
+            LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->comm.window);
+            cudaFree(ctx->comm.d_peer);
+            ctx->comm.window = nullptr;
+            ctx->comm.d_peer = nullptr;
+            ctx->comm.connected = false;
+        }
+        unsigned char handle[LDU_COMM_HANDLE_BYTES];
+        LDU_TRY(ldu_comm_window_create(ctx, 0, 1, (int)m->ifs.size(), maxN, handle));
+        LDU_TRY(ldu_comm_connect(ctx, handle));
+        ctx->comm.selfOnly = true;
+    }
     if ((int)m->ifs.size() > ctx->comm.maxInterfaces || maxN > ctx->comm.slotStride) {
         set_error("exchange window too small for this matrix's interfaces");
         return LDU_ECOMM;

@@ -303,6 +303,13 @@ static void build_row_views(ldu_matrix* m)
     }
     std::vector<int> fill(m->h_losortStart.begin(), m->h_losortStart.end() - 1);
     for (int f = 0; f < nf; f++) m->h_losort[fill[m->h_u[f]]++] = f;  // ascending f per cell
+    // are the faces of every owner also sorted by neighbour?  True for meshes in upper-triangular
+    // order; GAMG's coarse addressing numbers the faces of a coarse cell in order of discovery
+    // (GAMGAgglomerateLduAddressing.C:116-190), where a walk in losort order and a walk in face order
+    // visit the faces of one owner differently
+    m->nbrSorted = true;
+    for (int f = 1; f < nf && m->nbrSorted; f++)
+        if (m->h_l[f] == m->h_l[f - 1] && m->h_u[f] < m->h_u[f - 1]) m->nbrSorted = false;
 }
 
 int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lowerAddr,
@@ -461,6 +468,7 @@ int ldu_matrix_destroy(ldu_matrix* m)
     cudaFree(m->d_bRowStart);
     cudaFree(m->d_bEntry);
     cudaFree(m->d_cellBRow);
+    cudaFree(m->d_ownerByNbrDesc);
     flow_free(m);
     stencil_free(m);
     stencil2_free(m);

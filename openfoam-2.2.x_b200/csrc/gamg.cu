@@ -813,7 +813,9 @@ static int solve_coarsest(ldu_matrix* top, const ldu_controls* c, bool asPrecond
     ldu_matrix* cm = L->coarse;
     const double tol = asPrecond ? c->precTolerance : c->tolerance;
     const double relTol = asPrecond ? c->precRelTol : c->relTol;
-    if (cm->nIfFaces == 0 && cm->ctx->comm.nRanks == 1 && cm->nCells <= 8192) {
+    // LDU_GAMG_GENERIC_COARSEST=1 sends every coarsest level to the generic solver (tests)
+    const char* generic = getenv("LDU_GAMG_GENERIC_COARSEST");
+    if (cm->nIfFaces == 0 && cm->ctx->comm.nRanks == 1 && cm->nCells <= 8192 && !(generic && generic[0] == '1')) {
         CoarsestArgs a;
         a.n = cm->nCells;
         a.nf = cm->nFaces;

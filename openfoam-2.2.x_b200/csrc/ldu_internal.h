@@ -76,6 +76,7 @@ constexpr int kRedSlots = 8;       // doubles per reduction message
 struct Comm {
     int rank = 0, nRanks = 1;
     bool connected = false;
+    bool selfOnly = false;                        // window made by the library for cyclic-only matrices (comm.cu)
     unsigned char* window = nullptr;              // my window (device)
     size_t windowBytes = 0;
     int maxInterfaces = 0;                        // interface slots per rank
@@ -171,6 +172,10 @@ struct ldu_matrix {
     int* d_bRowCell = nullptr;     // [nBRows]
     int* d_bRowStart = nullptr;    // [nBRows+1]
     int* d_bEntry = nullptr;       // [nIfFaces] index into the concatenated arrays
+    // faces of every owner sorted by neighbour (upper-triangular order)?  If not (GAMG coarse levels),
+    // the reverse-losort walk of DILU's preconditionT needs its own per-row order (sweeps.cu)
+    bool nbrSorted = true;
+    int* d_ownerByNbrDesc = nullptr;   // [nFaces] faces of each owner range by descending neighbour (lazy)
     int ifBlockStart = 0;          // first cell on any interface (nonBlockingGaussSeidelSmoother.C:66-81)
     int* d_cellBRow = nullptr;     // [nCells] boundary row of a cell or -1 (lazy, nonBlockingGaussSeidel only)
     // sweep schedules (lazy)

@@ -329,7 +329,13 @@ int precond_apply(ldu_matrix* m, const Precond& p, double* wA, const double* rA,
     case LDU_PRECOND_DILU:
         if (!transpose)  // DILUPreconditioner.C:88-135
             return sweep_pair(m, p.rD, m->d_lower, m->d_upper, false, rA, wA, true);
-        // preconditionT: DILUPreconditioner.C:138-185
+        // preconditionT: DILUPreconditioner.C:138-185.  Its second loop walks the faces in reverse
+        // LOSORT order: on a matrix whose owner ranges are not sorted by neighbour (GAMG coarse
+        // levels) that is not the reverse face order of the other backward sweeps
+        if (!m->nbrSorted) {
+            LDU_TRY(sweep_forward(m, p.rD, m->d_upper, false, rA, wA, true));
+            return sweep_backward_losort(m, p.rD, m->d_lower, wA);
+        }
         return sweep_pair(m, p.rD, m->d_upper, m->d_lower, false, rA, wA, true);
     }
     return LDU_EINVAL;

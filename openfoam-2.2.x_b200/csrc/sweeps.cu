@@ -117,6 +117,25 @@ __global__ void __launch_bounds__(kBlock) bwd_level_kernel(
     w[c] = acc;
 }
 
+// the same with the faces of the row taken in a given order (perm[k], k over the owner range)
+__global__ void __launch_bounds__(kBlock) bwd_perm_level_kernel(
+    const SolverScalars* S, const int* __restrict__ rows, int nRows, const int* __restrict__ ownerStart,
+    const int* __restrict__ perm, const int* __restrict__ u, const double* __restrict__ rD,
+    const double* __restrict__ coef, double* __restrict__ w)
+{
+    if (S->done) return;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nRows) return;
+    const int c = rows[i];
+    const double rDc = rD[c];
+    double acc = w[c];
+    for (int k = ownerStart[c]; k < ownerStart[c + 1]; k++) {
+        const int f = perm[k];
+        acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(rDc, coef[f]), w[u[f]]));
+    }
+    w[c] = acc;
+}
+
 // calcReciprocalD, rows of one level (DICPreconditioner.C:66-74, DILU :66-75):
 //   rD[c] = diag[c];  for lower faces f (ascending): rD[c] -= upper[f]*lower[f]/rD[l[f]]
 // (the reciprocal is taken afterwards for all rows)
@@ -283,6 +302,28 @@ int sweep_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre
         LEVEL_LOOP(m->bwd, (bwd_level_kernel<false><<<grid, kBlock, 0, st>>>(
                                m->d_scalars, rows, nRows, m->d_ownerStart, m->d_u, rD, coef, w)));
     }
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+int sweep_backward_losort(ldu_matrix* m, const double* rD, const double* coef, double* w)
+{
+    if (m->nbrSorted) return sweep_backward(m, rD, coef, false, w);
+    LDU_TRY(build_schedules(m));
+    cudaStream_t st = m->ctx->stream;
+    if (!m->d_ownerByNbrDesc) {
+        // reverse losort order restricted to one owner = its faces by descending neighbour
+        std::vector<int> perm(m->nFaces);
+        for (int f = 0; f < m->nFaces; f++) perm[f] = f;
+        for (int c = 0; c < m->nCells; c++)
+            std::sort(perm.begin() + m->h_ownerStart[c], perm.begin() + m->h_ownerStart[c + 1],
+                      [&](int a, int b) { return m->h_u[a] > m->h_u[b]; });
+        LDU_CUDA(cudaMalloc((void**)&m->d_ownerByNbrDesc, std::max(m->nFaces, 1) * sizeof(int)));
+        LDU_CUDA(cudaMemcpyAsync(m->d_ownerByNbrDesc, perm.data(), m->nFaces * sizeof(int), cudaMemcpyHostToDevice, st));
+        LDU_CUDA(cudaStreamSynchronize(st));
+    }
+    LEVEL_LOOP(m->bwd, (bwd_perm_level_kernel<<<grid, kBlock, 0, st>>>(
+                           m->d_scalars, rows, nRows, m->d_ownerStart, m->d_ownerByNbrDesc, m->d_u, rD, coef, w)));
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;
 }

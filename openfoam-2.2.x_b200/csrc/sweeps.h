@@ -10,6 +10,10 @@ namespace ldu {
 int sweep_forward(ldu_matrix* m, const double* rD, const double* coef, bool pre, const double* r,
                   double* w, bool init);
 int sweep_backward(ldu_matrix* m, const double* rD, const double* coef, bool pre, double* w);
+// backward substitution that consumes the faces of a row in REVERSE LOSORT order (descending
+// neighbour): DILUPreconditioner::preconditionT's second loop (DILUPreconditioner.C:172-183).
+// Same as sweep_backward when m->nbrSorted.
+int sweep_backward_losort(ldu_matrix* m, const double* rD, const double* coef, double* w);
 int calc_reciprocal_D(ldu_matrix* m, double* rD, bool dilu);
 int calc_reciprocal_diag(ldu_matrix* m, double* rD);
 int calc_fdic_coeffs(ldu_matrix* m, const double* rD, double* rDuUpper, double* rDlUpper);

@@ -6,6 +6,7 @@
 #include "addToRunTimeSelectionTable.H"
 #include "Switch.H"
 #include "processorLduInterface.H"
+#include "cyclicLduInterface.H"
 #include "PstreamReduceOps.H"
 #include "UIPstream.H"
 #include "UOPstream.H"
@@ -120,15 +121,22 @@ ldu_context* context()
     return ctx;
 }
 
-// The coupled patches of a matrix as the C ABI wants them.  Processor patches only:
-// the other side lives on another rank (another GPU), faces in the same order on
-// both sides (processorLduInterface.H:88-97).
+// The coupled patches of a matrix as the C ABI wants them.  Processor patches: the
+// other side lives on another rank (another GPU), faces in the same order on both
+// sides (processorLduInterface.H:88-97).  Cyclic patches: the other half is a patch
+// of this very region (cyclicLduInterface.H:60-75), i.e. the neighbour rank is this
+// rank.  Transforming cyclics (rotational periodicity) do nothing to a scalar
+// (transformCoupleField with rank 0), which is all this solver sees.
 struct coupledPatches
 {
     DynamicList<label> patchIDs;      // interfaces_ index of compact interface i
     DynamicList<int> sizes;
     DynamicList<int> nbrRank;
+    DynamicList<label> nbrPatchID;    // cyclic: interfaces_ index of the other half, else -1
     DynamicList<const int*> faceCells;
+    bool anyProcessor;
+
+    coupledPatches() : anyProcessor(false) {}
 };
 
 void findCoupledPatches
@@ -142,17 +150,27 @@ void findCoupledPatches
     {
         if (!interfaces.set(patchi)) continue;
         const lduInterface& li = interfaces[patchi].interface();
-        if (!isA<processorLduInterface>(li))
+        const labelUList& fc = A.lduAddr().patchAddr(patchi);
+        if (isA<processorLduInterface>(li))
+        {
+            cp.nbrRank.append(refCast<const processorLduInterface>(li).neighbProcNo());
+            cp.nbrPatchID.append(-1);
+            cp.anyProcessor = true;
+        }
+        else if (isA<cyclicLduInterface>(li))
+        {
+            cp.nbrRank.append(Pstream::myProcNo());
+            cp.nbrPatchID.append(refCast<const cyclicLduInterface>(li).neighbPatchID());
+        }
+        else
         {
             FatalErrorIn("gpuLduSolver::solve")
                 << "coupled patch " << patchi << " of type " << li.type()
-                << ": only processor patches are handed to the GPU solver"
-                   " (cyclic patches: not yet)" << exit(FatalError);
+                << ": only processor and cyclic patches are handed to the GPU solver"
+                << exit(FatalError);
         }
-        const labelUList& fc = A.lduAddr().patchAddr(patchi);
         cp.patchIDs.append(patchi);
         cp.sizes.append(fc.size());
-        cp.nbrRank.append(refCast<const processorLduInterface>(li).neighbProcNo());
         cp.faceCells.append(fc.begin());
     }
 }
@@ -251,10 +269,21 @@ ldu_matrix* deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
     // index of the matching interface in the neighbour's (compact) list: each side
     // tells the other (patches towards one neighbour are in the same order on both sides)
     List<int> nbrInterface(cp.sizes.size(), 0);
-    if (cp.sizes.size())
+    if (Pstream::parRun())
     {
+        // collective, also for a rank whose own patches are all cyclic
         connectDevices(cp);
-        forAll(nbrInterface, i)
+    }
+    forAll(nbrInterface, i)
+    {
+        if (cp.nbrPatchID[i] >= 0)
+        {
+            forAll(cp.patchIDs, j)
+            {
+                if (cp.patchIDs[j] == cp.nbrPatchID[i]) nbrInterface[i] = j;
+            }
+        }
+        else
         {
             const int mine = i;
             UOPstream::write
@@ -263,7 +292,10 @@ ldu_matrix* deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
                 reinterpret_cast<const char*>(&mine), sizeof(int)
             );
         }
-        forAll(nbrInterface, i)
+    }
+    forAll(nbrInterface, i)
+    {
+        if (cp.nbrPatchID[i] < 0)
         {
             UIPstream::read
             (

@@ -344,16 +344,19 @@ def _write_problem(path, sysd, psi=None, source=None):
             _f64(sysd["faceWeights"]).tofile(fh)
 
 
-def ref_run(sysd, op, *args, psi=None, source=None, ints=False, timeout=3600):
-    """Run the unmodified reference on a single-region system.
-    Returns (array, stdout)."""
-    env = dict(os.environ, WM_PROJECT_DIR=str(HERE / "_ref"))
+def ref_run(sysd, op, *args, psi=None, source=None, ints=False, timeout=3600, extra_env=None):
+    """Run the unmodified reference on a single-region system (cyclic interfaces allowed:
+    interfaces with nbrRegion 0).  Returns (array, stdout)."""
+    env = dict(os.environ, WM_PROJECT_DIR=str(HERE / "_ref"), **(extra_env or {}))
     ld = env.get("LD_LIBRARY_PATH", "")
     env["LD_LIBRARY_PATH"] = str(HERE / "_ref") + (":" + ld if ld else "")
     with tempfile.TemporaryDirectory() as td:
         prob = os.path.join(td, "p.bin")
         outp = os.path.join(td, "o.bin")
-        _write_problem(prob, sysd, psi=psi, source=source)
+        if sysd.get("interfaces"):
+            _write_region(prob, sysd, psi=psi, source=source)
+        else:
+            _write_problem(prob, sysd, psi=psi, source=source)
         r = subprocess.run([str(REF_DRIVER), prob, outp, op, *[str(a) for a in args]],
                            env=env, capture_output=True, text=True, timeout=timeout, cwd=td)
         if r.returncode != 0:
@@ -370,8 +373,9 @@ def ref_par_available() -> bool:
     return REF_DRIVER_PAR.exists() and (HERE / "_ref" / "libPstream_shm.so").exists()
 
 
-def _write_region(path, reg, psi=None, source=None):
-    """'LDU2' problem file of one mesh region (oracle/ref_driver.C header)."""
+def _write_region(path, reg, psi=None, source=None, rank=0):
+    """'LDU2' problem file of one mesh region (oracle/ref_driver.C header).  An interface whose
+    neighbour is the region itself is one half of a cyclic pair."""
     asym = reg.get("lowerCoef") is not None
     weights = reg.get("faceWeights") is not None
     n = np.asarray(reg["diag"]).size
@@ -391,7 +395,8 @@ def _write_region(path, reg, psi=None, source=None):
             _f64(reg["faceWeights"]).tofile(fh)
         for it in its:
             fc = np.asarray(it["faceCells"], dtype=np.int32)
-            np.array([it["nbrRegion"], fc.size], dtype=np.int32).tofile(fh)
+            nbr = it["nbrRegion"] if it["nbrRegion"] != rank else -1 - it["nbrInterface"]
+            np.array([nbr, fc.size], dtype=np.int32).tofile(fh)
             fc.tofile(fh)
             _f64(it["bouCoeffs"]).tofile(fh)
             _f64(it["intCoeffs"]).tofile(fh)
@@ -410,7 +415,7 @@ def ref_run_par(regions, op, *args, psi=None, source=None, ints=False, timeout=3
         seg.truncate(_SHM_WORLD_BYTES)
         seg.flush()
         for r, reg in enumerate(regions):
-            _write_region(os.path.join(td, f"p{r}.bin"), reg,
+            _write_region(os.path.join(td, f"p{r}.bin"), reg, rank=r,
                           psi=None if psi is None else psi[r], source=None if source is None else source[r])
         procs = []
         for r in range(n):

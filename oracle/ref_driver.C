@@ -35,9 +35,13 @@
   after the header one extra int32 nInterfaces and, at the end,
       per interface: int32 nbrRank, int32 size, int32 faceCells[size],
                      f64 bouCoeffs[size], f64 intCoeffs[size]
-  The interfaces are processor interfaces (classes below) doing what
-  processorFvPatch / processorFvPatchField<scalar> do in libfiniteVolume
+  nbrRank >= 0: a processor interface (classes below) doing what processorFvPatch /
+  processorFvPatchField<scalar> do in libfiniteVolume
   (finiteVolume/fields/fvPatchFields/constraint/processor/processorFvPatchScalarField.C:33-116).
+  nbrRank < 0: one half of a cyclic pair inside this region whose other half is interface
+  -1 - nbrRank (cyclicFvPatch / cyclicFvPatchField<scalar>::updateInterfaceMatrix,
+  finiteVolume/fields/fvPatchFields/constraint/cyclic/cyclicFvPatchField.C:174-197).
+  The serial binary reads 'LDU2' files too (cyclic interfaces only).
 
   Reference entry points exercised (all in /root/reference/src/OpenFOAM):
       lduMatrix::Amul/Tmul/sumA/residual   matrices/lduMatrix/lduMatrix/lduMatrixATmul.C:34-295
@@ -58,6 +62,8 @@
 #include "PCG.H"
 #include "processorLduInterface.H"
 #include "processorLduInterfaceField.H"
+#include "cyclicLduInterface.H"
+#include "cyclicLduInterfaceField.H"
 #include "IPstream.H"
 #include "OPstream.H"
 #include "dlLibraryTable.H"
@@ -297,6 +303,114 @@ public:
 defineTypeNameAndDebug(flatProcessorInterfaceField, 0);
 }
 
+
+// One half of a cyclic (periodic) pair of a flat LDU region, no transformation.
+// Type name "cyclic": the coarse levels get cyclicGAMGInterface(Field)
+// (cyclicGAMGInterface.C:47-119, cyclicGAMGInterfaceField.C:66-89).
+namespace Foam
+{
+class flatCyclicInterface
+:
+    public lduInterface,
+    public cyclicLduInterface
+{
+    labelList faceCells_;
+    label index_;
+    label nbrIndex_;
+    const lduInterfacePtrsList& all_;
+    tensorField noTransform_;
+
+public:
+    TypeName("cyclic");
+
+    flatCyclicInterface
+    (
+        const labelList& fc,
+        const label index,
+        const label nbrIndex,
+        const lduInterfacePtrsList& all
+    )
+    :
+        faceCells_(fc),
+        index_(index),
+        nbrIndex_(nbrIndex),
+        all_(all),
+        noTransform_(0)
+    {}
+
+    virtual const labelUList& faceCells() const { return faceCells_; }
+    virtual label neighbPatchID() const { return nbrIndex_; }
+    virtual bool owner() const { return index_ < nbrIndex_; }
+    virtual const cyclicLduInterface& neighbPatch() const
+    {
+        return refCast<const cyclicLduInterface>(all_[nbrIndex_]);
+    }
+    virtual const tensorField& forwardT() const { return noTransform_; }
+    virtual const tensorField& reverseT() const { return noTransform_; }
+
+    virtual tmp<labelField> interfaceInternalField(const labelUList& iF) const
+    {
+        tmp<labelField> tf(new labelField(faceCells_.size()));
+        labelField& pf = tf();
+        forAll(pf, i) pf[i] = iF[faceCells_[i]];
+        return tf;
+    }
+
+    // the other half's cells, same region: no transfer needed
+    virtual tmp<labelField> internalFieldTransfer
+    (
+        const Pstream::commsTypes,
+        const labelUList& iF
+    ) const
+    {
+        return all_[nbrIndex_].interfaceInternalField(iF);
+    }
+};
+
+defineTypeNameAndDebug(flatCyclicInterface, 0);
+
+
+class flatCyclicInterfaceField
+:
+    public lduInterfaceField,
+    public cyclicLduInterfaceField
+{
+    const flatCyclicInterface& patch_;
+
+public:
+    TypeName("cyclic");
+
+    flatCyclicInterfaceField(const flatCyclicInterface& p)
+    :
+        lduInterfaceField(p),
+        patch_(p)
+    {}
+
+    virtual bool doTransform() const { return false; }
+    virtual const tensorField& forwardT() const { return patch_.forwardT(); }
+    virtual const tensorField& reverseT() const { return patch_.reverseT(); }
+    virtual int rank() const { return 0; }
+
+    // result[faceCell] -= coeff*psi[cell behind the other half]
+    virtual void updateInterfaceMatrix
+    (
+        scalarField& result,
+        const scalarField& psiInternal,
+        const scalarField& coeffs,
+        const direction,
+        const Pstream::commsTypes
+    ) const
+    {
+        const labelUList& nbrCells =
+            dynamic_cast<const lduInterface&>(patch_.neighbPatch()).faceCells();
+        const labelUList& fc = patch_.faceCells();
+        forAll(fc, i) result[fc[i]] -= coeffs[i]*psiInternal[nbrCells[i]];
+    }
+};
+
+defineTypeNameAndDebug(flatCyclicInterfaceField, 0);
+}
+
 static dictionary dictFromText(const std::string& text)
 {
     IStringStream is(text);
@@ -378,8 +492,8 @@ int main(int argc, char* argv[])
         readOrDie(faceWeights.begin(), sizeof(scalar), nFaces, f);
         gFaceWeights = &faceWeights;
     }
-    PtrList<flatProcessorInterface> procPatches(nInterfaces);
-    PtrList<flatProcessorInterfaceField> procFields(nInterfaces);
+    PtrList<lduInterface> patches(nInterfaces);
+    PtrList<lduInterfaceField> patchFields(nInterfaces);
     labelListList patchAddr(nInterfaces);
     lduInterfacePtrsList meshInterfaces(nInterfaces);
     lduSchedule schedule(2*nInterfaces);
@@ -396,10 +510,21 @@ int main(int argc, char* argv[])
         intCoeffs.set(i, new scalarField(ih[1]));
         readOrDie(bouCoeffs[i].begin(), sizeof(scalar), ih[1], f);
         readOrDie(intCoeffs[i].begin(), sizeof(scalar), ih[1], f);
-        procPatches.set(i, new flatProcessorInterface(patchAddr[i], ih[0]));
-        procFields.set(i, new flatProcessorInterfaceField(procPatches[i]));
-        meshInterfaces.set(i, &procPatches[i]);
-        interfaces.set(i, &procFields[i]);
+        if (ih[0] >= 0)
+        {
+            flatProcessorInterface* pp = new flatProcessorInterface(patchAddr[i], ih[0]);
+            patches.set(i, pp);
+            patchFields.set(i, new flatProcessorInterfaceField(*pp));
+        }
+        else
+        {
+            flatCyclicInterface* cp =
+                new flatCyclicInterface(patchAddr[i], i, -1 - ih[0], meshInterfaces);
+            patches.set(i, cp);
+            patchFields.set(i, new flatCyclicInterfaceField(*cp));
+        }
+        meshInterfaces.set(i, &patches[i]);
+        interfaces.set(i, &patchFields[i]);
         schedule[2*i].patch = i;
         schedule[2*i].init = true;
         schedule[2*i + 1].patch = i;

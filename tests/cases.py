@@ -126,6 +126,74 @@ def regions(name, n_regions, partition):
     return s, decompose.decompose(s, proc, n_regions)
 
 
+# periodic (cyclic) cases: (system, axis, controls) for one region, (system, regions, axis, controls)
+# for z-slab regions that are each periodic along `axis`
+CYCLIC_SYSTEMS = [("box12_var", 0), ("asym10", 1), ("cavity20x20", 1), ("box6x40x9", 2)]
+CYCLIC_SOLVES = [
+    ("box12_var", 0, dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)),
+    ("cavity20x20", 1, dict(solver="PCG", preconditioner="FDIC", tolerance=1e-8, relTol=0)),
+    ("asym10", 1, dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)),
+    ("box6x40x9", 2, dict(solver="smoothSolver", smoother="symGaussSeidel", nSweeps=2, tolerance=1e-6,
+                          relTol=0, maxIter=60)),
+    ("box12_var", 0, dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0)),
+    ("asym10", 1, dict(_GAMG, smoother="DILU", agglomerator="algebraicPair", tolerance=1e-8, relTol=0)),
+    ("box6x40x9", 2, dict(_GAMG, smoother="nonBlockingGaussSeidel", agglomerator="faceAreaPair", mergeLevels=2,
+                          tolerance=1e-8, relTol=0)),
+]
+CYCLIC_REGION_SOLVES = [
+    ("box12_var", 3, 0, dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)),
+    ("asym10", 2, 1, dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)),
+    ("box12_var", 2, 1, dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0)),
+    ("asym10", 2, 0, dict(solver="smoothSolver", smoother="nonBlockingGaussSeidel", nSweeps=2, tolerance=1e-6,
+                          relTol=0, maxIter=40)),
+]
+
+
+def _add_cyclic(reg, region, gcells, dims, axis, up, lo):
+    """append the two halves of a cyclic pair along `axis` to region dict `reg` (cells given by their
+    global index gcells in the nx*ny*nz box): end plane 0 is the owner half, plane n-1 the other."""
+    nx, ny, nz = dims
+    coord = (gcells % nx, (gcells // nx) % ny, gcells // (nx * ny))[axis]
+    a = np.nonzero(coord == 0)[0]
+    b = np.nonzero(coord == dims[axis] - 1)[0]
+    assert a.size == b.size and a.size > 0
+    k = 0.6 + 0.3 * np.sin(0.9 * np.arange(a.size))            # coupling coefficient per face pair
+    ku, kl = up * k, lo * k
+    reg["diag"] = reg["diag"].copy()
+    reg["diag"][a] -= ku
+    reg["diag"][b] -= ku
+    first = len(reg["interfaces"])
+    reg["interfaces"].append(dict(nbrRegion=region, nbrInterface=first + 1, faceCells=a.astype(np.int32),
+                                  bouCoeffs=-ku, intCoeffs=-kl))
+    reg["interfaces"].append(dict(nbrRegion=region, nbrInterface=first, faceCells=b.astype(np.int32),
+                                  bouCoeffs=-kl, intCoeffs=-ku))
+
+
+def cyclic_system(name, axis=0):
+    """box system `name` made periodic along `axis`: its two end planes become the halves of a cyclic
+    patch pair, i.e. two interfaces of the single region that point at each other."""
+    kw = SYSTEMS[name]
+    s = dict(system(name))
+    s["interfaces"] = []
+    asym = s["lowerCoef"] is not None
+    _add_cyclic(s, 0, np.arange(s["nCells"]), (kw["nx"], kw["ny"], kw["nz"]), axis, 1.0, 0.8 if asym else 1.0)
+    return s
+
+
+def cyclic_regions(name, n_regions, axis=0):
+    """box system `name` cut into z-slabs (one region per rank), every region periodic along `axis`:
+    processor interfaces between the slabs plus a cyclic pair inside each region."""
+    from ldub200 import decompose
+    kw = SYSTEMS[name]
+    dims = (kw["nx"], kw["ny"], kw["nz"])
+    s = system(name)
+    regs = decompose.decompose(s, decompose.block_partition(*dims, 1, 1, n_regions), n_regions)
+    asym = s["lowerCoef"] is not None
+    for r, reg in enumerate(regs):
+        _add_cyclic(reg, r, reg["cells"], dims, axis, 1.0, 0.8 if asym else 1.0)
+    return s, regs
+
+
 PRECONDITIONERS = ["none", "diagonal", "DIC", "FDIC", "DILU"]
 SMOOTHERS = ["GaussSeidel", "symGaussSeidel", "DIC", "DILU", "FDIC", "DICGaussSeidel",
              "DILUGaussSeidel", "nonBlockingGaussSeidel"]

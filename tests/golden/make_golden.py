@@ -89,6 +89,26 @@ def main():
                 out = O.ref_run_par(regs, "smooth", O.dict_text(dict(smoother=sm)), 2, psi=xs)[0]
                 multi[f"{key}_smooth_{sm}"] = decompose.gather_field(regs, out, s["nCells"])
     np.savez_compressed(HERE / "multi_region.npz", **multi)
+    # cyclic (periodic) patches, one region
+    cyc = {}
+    for name, axis in cases.CYCLIC_SYSTEMS[:3]:
+        s = cases.cyclic_system(name, axis)
+        x = rng.standard_normal(s["nCells"])
+        key = f"{name}_{axis}"
+        cyc[key + "_x"] = x
+        for op in ("amul", "tmul", "suma", "residual"):
+            cyc[f"{key}_{op}"] = O.ref_run(s, op, psi=x)[0]
+        for sm in cases.SMOOTHERS:
+            if cases.selectable(s, sm):
+                cyc[f"{key}_smooth_{sm}"] = O.ref_run(s, "smooth", O.dict_text(dict(smoother=sm)), 2, psi=x)[0]
+    for i, (name, axis, ctl) in enumerate(cases.CYCLIC_SOLVES):
+        s = cases.cyclic_system(name, axis)
+        psi, perf = O.ref_solve(s, cases.ref_controls(ctl))
+        cyc[f"psi_{i}"] = psi
+        cyc[f"perf_{i}"] = np.array([perf["initialResidual"], perf["finalResidual"],
+                                     perf["nIterations"], perf["converged"], perf["singular"]], dtype=np.float64)
+        print("cyclic solve", i, name, ctl["solver"], perf["nIterations"])
+    np.savez_compressed(HERE / "cyclic.npz", **cyc)
     print("multi-region", len(multi))
 
 

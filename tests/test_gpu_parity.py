@@ -32,8 +32,14 @@ def _oracle():
 
 def _matrix(ctx, s):
     import ldub200
-    A = ldub200.lduMatrix(ctx, s["nCells"], s["lower"], s["upper"])
-    A.set_coeffs(s["diag"], s["upperCoef"], s["lowerCoef"])
+    its = s.get("interfaces") or []
+    ifs = [ldub200.lduInterface(it["faceCells"], it["nbrRegion"], it["nbrInterface"]) for it in its]
+    A = ldub200.lduMatrix(ctx, s["nCells"], s["lower"], s["upper"], ifs)
+    if its:
+        A.set_coeffs(s["diag"], s["upperCoef"], s["lowerCoef"], [it["bouCoeffs"] for it in its],
+                     [it["intCoeffs"] for it in its])
+    else:
+        A.set_coeffs(s["diag"], s["upperCoef"], s["lowerCoef"])
     if s.get("faceWeights") is not None:
         A.set_face_weights(s["faceWeights"])
     return A
@@ -279,3 +285,66 @@ def test_large_box_properties(ctx):
     hist = A.residual_history()
     assert len(hist) == perf.nIterations + 1 and hist[-1] == perf.finalResidual
     A.destroy()
+
+
+# --- cyclic (periodic) patches: interfaces whose neighbour is the region itself; a single process
+# --- needs no ldu_comm_connect for them (the library is its own only peer)
+@pytest.mark.parametrize("name,axis", cases.CYCLIC_SYSTEMS)
+def test_cyclic_operators_and_smoothers_bit_exact(ctx, name, axis):
+    import ldub200
+    s = cases.cyclic_system(name, axis)
+    O = _oracle()
+    w = O.World([s])
+    A = _matrix(ctx, s)
+    x = np.random.default_rng(11).standard_normal(s["nCells"])
+    assert np.array_equal(A.Amul(x), w.amul(x)[0])
+    assert np.array_equal(A.Tmul(x), w.tmul(x)[0])
+    assert np.array_equal(A.sumA(), w.sumA()[0])
+    assert np.array_equal(A.residual(x, s["source"]), w.residual(x, s["source"])[0])
+    for sm in cases.SMOOTHERS:
+        if cases.selectable(s, sm):
+            psi = x.copy()
+            ldub200.lduMatrix.smoother.New("p", A, sm).smooth(psi, s["source"], 3)
+            assert np.array_equal(psi, w.smooth(sm, x, s["source"], 3)[0]), sm
+    A.destroy()
+
+
+@pytest.mark.parametrize("case", range(len(cases.CYCLIC_SOLVES)))
+def test_cyclic_solves_bit_exact(ctx, case):
+    import ldub200
+    name, axis, ctl = cases.CYCLIC_SOLVES[case]
+    s = cases.cyclic_system(name, axis)
+    O = _oracle()
+    psi_o, perf_o = O.World([s]).solve(ctl, s["psi0"], s["source"])
+    A = _matrix(ctx, s)
+    psi = s["psi0"].copy()
+    perf = ldub200.lduMatrix.solver.New("p", A, ctl).solve(psi, s["source"])
+    assert perf.nIterations == perf_o["nIterations"], (str(perf), perf_o)
+    psi = s["psi0"].copy()
+    perf = ldub200.lduMatrix.solver.New("p", A, dict(ctl, referenceOrderSums=True)).solve(psi, s["source"])
+    assert perf.nIterations == perf_o["nIterations"]
+    assert perf.finalResidual == perf_o["finalResidual"]
+    assert np.array_equal(psi, psi_o[0])
+    A.destroy()
+
+
+def test_generic_coarsest_solver_bit_exact(ctx, monkeypatch):
+    """With interfaces or several ranks the coarsest GAMG level goes to the generic PBiCG+DILU /
+    PCG+DIC solver instead of the single-thread kernel.  GAMG's coarse addressing does not sort the
+    faces of a cell by neighbour, so DILU's preconditionT (reverse losort walk) needs its own row
+    order there: forced here on a matrix without interfaces."""
+    import ldub200
+    monkeypatch.setenv("LDU_GAMG_GENERIC_COARSEST", "1")
+    for name, sm in [("asym10", "GaussSeidel"), ("asym10", "DILU"), ("box12_var", "GaussSeidel")]:
+        s = cases.system(name)
+        ctl = dict(solver="GAMG", smoother=sm, agglomerator="algebraicPair", nCellsInCoarsestLevel=10,
+                   mergeLevels=1, cacheAgglomeration=False, tolerance=1e-8, relTol=0)
+        O = _oracle()
+        psi_o, perf_o = O.World([s]).solve(ctl, s["psi0"], s["source"])
+        A = _matrix(ctx, s)
+        psi = s["psi0"].copy()
+        perf = ldub200.lduMatrix.solver.New("p", A, dict(ctl, referenceOrderSums=True)).solve(psi, s["source"])
+        assert perf.nIterations == perf_o["nIterations"]
+        assert perf.finalResidual == perf_o["finalResidual"], (name, sm)
+        assert np.array_equal(psi, psi_o[0]), (name, sm)
+        A.destroy()

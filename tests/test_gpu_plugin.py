@@ -91,6 +91,9 @@ def run_par(regs, controls, plugin):
     ("box40x30x20", 4, "slab", dict(solver="GAMG", smoother="GaussSeidel", agglomerator="algebraicPair",
                                      nCellsInCoarsestLevel=10, mergeLevels=1, cacheAgglomeration=False,
                                      tolerance=1e-8, relTol=0)),
+    ("asym33x17x11", 3, "slab", dict(solver="GAMG", smoother="DILU", agglomerator="algebraicPair",
+                                      nCellsInCoarsestLevel=10, mergeLevels=1, cacheAgglomeration=False,
+                                      tolerance=1e-8, relTol=0)),
 ])
 def test_plugin_multi_rank_bit_identical(name, R, part, controls):
     import numpy as np
@@ -109,3 +112,34 @@ def test_plugin_multi_rank_bit_identical(name, R, part, controls):
     psi_fast, perf_fast = run_par(regs, dict(controls, solver=gpu[controls["solver"]]), plugin=True)
     assert perf_fast["nIterations"] == perf_ref["nIterations"]
     assert abs(perf_fast["finalResidual"] - perf_ref["finalResidual"]) <= 1e-4 * perf_ref["finalResidual"] + 1e-13
+
+
+def test_plugin_cyclic_patches_serial():
+    """a serial case with a cyclic patch pair: the plug-in turns cyclicLduInterface into interfaces
+    whose neighbour is the region itself"""
+    import numpy as np
+    if not (PLUGIN.exists() and O.ref_available()):
+        pytest.skip("plug-in / reference binaries not built")
+    s = cases.cyclic_system("box12_var", 0)
+    for ctl, gpu in [(dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0), "gpuPCG"),
+                     (dict(solver="GAMG", smoother="GaussSeidel", agglomerator="algebraicPair",
+                           nCellsInCoarsestLevel=10, mergeLevels=1, cacheAgglomeration=False,
+                           tolerance=1e-8, relTol=0), "gpuGAMG")]:
+        psi_ref, so = O.ref_run(s, "solve", O.dict_text(ctl))
+        psi_gpu, so_gpu = O.ref_run(s, "solve", O.dict_text(dict(ctl, solver=gpu, referenceOrderSums=True)),
+                                    extra_env=dict(LDU_REF_LIBS=str(PLUGIN)))
+        assert O.parse_perf(so_gpu)["nIterations"] == O.parse_perf(so)["nIterations"]
+        assert O.parse_perf(so_gpu)["finalResidual"] == O.parse_perf(so)["finalResidual"]
+        assert np.array_equal(psi_gpu, psi_ref)
+
+
+def test_plugin_multi_rank_with_cyclic_patches():
+    import numpy as np
+    s, regs = cases.cyclic_regions("box12_var", 2, 0)
+    ctl = dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)
+    psi_ref, perf_ref = run_par(regs, ctl, plugin=False)
+    psi_gpu, perf_gpu = run_par(regs, dict(ctl, solver="gpuPCG", referenceOrderSums=True), plugin=True)
+    assert perf_gpu["nIterations"] == perf_ref["nIterations"]
+    assert perf_gpu["finalResidual"] == perf_ref["finalResidual"]
+    for a, b in zip(psi_gpu, psi_ref):
+        assert np.array_equal(a, b)

@@ -120,3 +120,37 @@ def test_multi_region_operators_and_smoothers(name, R, part):
             assert np.array_equal(gathered(w.smooth(sm, xs, src, 2)), g[k]), sm
             checked += 1
     assert checked >= 5
+
+
+# --- cyclic (periodic) patches
+@pytest.mark.parametrize("name,axis", cases.CYCLIC_SYSTEMS[:3])
+def test_cyclic_operators_and_smoothers(name, axis):
+    g = np.load(GOLD / "cyclic.npz")
+    s = cases.cyclic_system(name, axis)
+    key = f"{name}_{axis}"
+    x = g[key + "_x"]
+    w = O.World([s])
+    assert np.array_equal(w.amul(x)[0], g[key + "_amul"])
+    assert np.array_equal(w.tmul(x)[0], g[key + "_tmul"])
+    assert np.array_equal(w.sumA()[0], g[key + "_suma"])
+    assert np.array_equal(w.residual(x, s["source"])[0], g[key + "_residual"])
+    checked = 0
+    for k in g.files:
+        if k.startswith(key + "_smooth_"):
+            sm = k[len(key) + 8:]
+            assert np.array_equal(w.smooth(sm, x, s["source"], 2)[0], g[k]), sm
+            checked += 1
+    assert checked >= 5
+
+
+@pytest.mark.parametrize("case", range(len(cases.CYCLIC_SOLVES)))
+def test_cyclic_solves(case):
+    g = np.load(GOLD / "cyclic.npz")
+    name, axis, ctl = cases.CYCLIC_SOLVES[case]
+    s = cases.cyclic_system(name, axis)
+    psi, perf = O.World([s]).solve(ctl, s["psi0"], s["source"])
+    ref = g[f"perf_{case}"]
+    assert perf["initialResidual"] == ref[0]
+    assert perf["finalResidual"] == ref[1]
+    assert perf["nIterations"] == int(ref[2])
+    assert np.array_equal(psi[0], g[f"psi_{case}"])

@@ -76,3 +76,32 @@ def test_agglomeration(name, merge, weights):
     for a, b in zip(mine, ref):
         assert a["nCoarse"] == b["nCoarse"]
         assert np.array_equal(a["restrict"], b["restrict"])
+
+
+# --- cyclic (periodic) patches: two interfaces of the one region pointing at each other; the driver
+# --- gives the reference cyclicLduInterface(Field) objects of type "cyclic" (oracle/ref_driver.C)
+@pytest.mark.parametrize("name,axis", cases.CYCLIC_SYSTEMS)
+def test_cyclic_operators_and_smoothers(name, axis):
+    s = cases.cyclic_system(name, axis)
+    w = O.World([s])
+    x = np.random.default_rng(5).standard_normal(s["nCells"])
+    assert np.array_equal(w.amul(x)[0], O.ref_run(s, "amul", psi=x)[0])
+    assert np.array_equal(w.tmul(x)[0], O.ref_run(s, "tmul", psi=x)[0])
+    assert np.array_equal(w.sumA()[0], O.ref_run(s, "suma")[0])
+    assert np.array_equal(w.residual(x, s["source"])[0], O.ref_run(s, "residual", psi=x)[0])
+    for sm in cases.SMOOTHERS:
+        if cases.selectable(s, sm):
+            want, _ = O.ref_run(s, "smooth", O.dict_text(dict(smoother=sm)), 3, psi=x)
+            assert np.array_equal(w.smooth(sm, x, s["source"], 3)[0], want), sm
+
+
+@pytest.mark.parametrize("case", range(len(cases.CYCLIC_SOLVES)))
+def test_cyclic_solves(case):
+    name, axis, ctl = cases.CYCLIC_SOLVES[case]
+    s = cases.cyclic_system(name, axis)
+    psi_o, perf_o = O.World([s]).solve(ctl, s["psi0"], s["source"])
+    psi_r, perf_r = O.ref_solve(s, cases.ref_controls(ctl))
+    assert perf_o["nIterations"] == perf_r["nIterations"]
+    assert perf_o["initialResidual"] == perf_r["initialResidual"]
+    assert perf_o["finalResidual"] == perf_r["finalResidual"]
+    assert np.array_equal(psi_o[0], psi_r)

@@ -72,3 +72,20 @@ def test_agglomeration(name, R, merge, weights):
             assert mine[lev]["nCoarse"] == nc
             assert np.array_equal(mine[lev]["restrict"], out[r][pos + 2:pos + 2 + nf])
             pos += 2 + nf
+
+
+@pytest.mark.parametrize("case", range(len(cases.CYCLIC_REGION_SOLVES)))
+def test_regions_with_cyclic_patches(case):
+    """processor interfaces between the slabs AND a cyclic pair inside every region"""
+    name, R, axis, ctl = cases.CYCLIC_REGION_SOLVES[case]
+    s, regs = cases.cyclic_regions(name, R, axis)
+    w = O.World(regs)
+    x = np.random.default_rng(9).standard_normal(s["nCells"])
+    xs = [x[r["cells"]] for r in regs]
+    assert same(w.amul(xs), O.ref_run_par(regs, "amul", psi=xs)[0])
+    psi_o, perf_o = w.solve(ctl, [r["psi0"] for r in regs], [r["source"] for r in regs])
+    psi_r, so = O.ref_run_par(regs, "solve", O.dict_text(cases.ref_controls(ctl)))
+    perf_r = O.parse_perf(so)
+    assert perf_o["nIterations"] == perf_r["nIterations"]
+    assert perf_o["finalResidual"] == perf_r["finalResidual"]
+    assert same(psi_o, psi_r)
