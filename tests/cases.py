@@ -149,6 +149,38 @@ CYCLIC_REGION_SOLVES = [
 ]
 
 
+# a real unstructured mesh: the polyMesh shipped with the reference's airFoil2D tutorial (10,720 cells,
+# 21,254 internal faces), read by ldub200.polymesh; tests/golden/airfoil2d.npz carries the system built
+# from it and the reference's results, so the tests run where /root/reference is absent
+AIRFOIL_POLYMESH = "/root/reference/tutorials/incompressible/simpleFoam/airFoil2D/constant/polyMesh"
+AIRFOIL_SOLVES = [
+    dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0),
+    dict(solver="PCG", preconditioner="FDIC", tolerance=1e-6, relTol=0),
+    dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-7, relTol=0, maxIter=60),
+    dict(solver="smoothSolver", smoother="symGaussSeidel", nSweeps=2, tolerance=1e-6, relTol=0, maxIter=30),
+]
+
+
+def digest(a):
+    """SHA-256 of an array's bytes as a uint8 array (bit-exact comparison in a small fixture)"""
+    import hashlib
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, dtype=np.float64).tobytes()).digest(), dtype=np.uint8)
+
+
+def airfoil_x(n):
+    return np.sin(0.11 * np.arange(n)) + 0.3 * np.cos(0.013 * np.arange(n))
+
+
+def airfoil_system():
+    """the airFoil2D Laplacian system from the committed fixture (same dict layout as system())"""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "airfoil2d.npz")
+    n = g["diag"].size
+    return dict(nCells=n, nFaces=g["lower"].size, lower=g["lower"], upper=g["upper"], diag=g["diag"],
+                upperCoef=g["upperCoef"], lowerCoef=None, source=g["source"], psi0=np.zeros(n),
+                faceWeights=g["faceWeights"]), g
+
+
 def _add_cyclic(reg, region, gcells, dims, axis, up, lo):
     """append the two halves of a cyclic pair along `axis` to region dict `reg` (cells given by their
     global index gcells in the nx*ny*nz box): end plane 0 is the owner half, plane n-1 the other."""

@@ -109,6 +109,29 @@ def main():
                                      perf["nIterations"], perf["converged"], perf["singular"]], dtype=np.float64)
         print("cyclic solve", i, name, ctl["solver"], perf["nIterations"])
     np.savez_compressed(HERE / "cyclic.npz", **cyc)
+    # a real unstructured mesh: the polyMesh the reference ships with the airFoil2D tutorial, read by
+    # ldub200.polymesh; Laplacian coefficients from its geometry; solved by the reference
+    from ldub200 import polymesh
+    mesh = polymesh.read_poly_mesh(cases.AIRFOIL_POLYMESH, geometry=True)
+    s = polymesh.laplacian_system(mesh, variable=True)
+    air = dict(lower=s["lower"], upper=s["upper"], diag=s["diag"], upperCoef=s["upperCoef"],
+               faceWeights=s["faceWeights"], source=s["source"])
+    # outputs are kept as SHA-256 digests of their bytes (bit-exact comparison, small fixture);
+    # the first solution in full
+    x = cases.airfoil_x(s["nCells"])
+    air["sha_amul"] = cases.digest(O.ref_run(s, "amul", psi=x)[0])
+    air["sha_smooth_GaussSeidel"] = cases.digest(
+        O.ref_run(s, "smooth", O.dict_text(dict(smoother="GaussSeidel")), 2, psi=x)[0])
+    air["sha_pre_DIC"] = cases.digest(O.ref_run(s, "precondition", "DIC")[0])
+    for i, ctl in enumerate(cases.AIRFOIL_SOLVES):
+        psi, perf = O.ref_solve(s, cases.ref_controls(ctl))
+        if i == 0:
+            air["psi_0"] = psi
+        air[f"sha_psi_{i}"] = cases.digest(psi)
+        air[f"perf_{i}"] = np.array([perf["initialResidual"], perf["finalResidual"],
+                                     perf["nIterations"], perf["converged"], perf["singular"]], dtype=np.float64)
+        print("airFoil2D solve", i, ctl["solver"], perf["nIterations"])
+    np.savez_compressed(HERE / "airfoil2d.npz", **air)
     print("multi-region", len(multi))
 
 

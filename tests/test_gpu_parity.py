@@ -348,3 +348,29 @@ def test_generic_coarsest_solver_bit_exact(ctx, monkeypatch):
         assert perf.finalResidual == perf_o["finalResidual"], (name, sm)
         assert np.array_equal(psi, psi_o[0]), (name, sm)
         A.destroy()
+
+
+def test_airfoil_real_unstructured_mesh(ctx):
+    """the polyMesh of the reference's airFoil2D tutorial (imported by ldub200.polymesh, committed as
+    tests/golden/airfoil2d.npz): operators and solves against the REFERENCE's own committed results"""
+    import ldub200
+    s, g = cases.airfoil_system()
+    A = _matrix(ctx, s)
+    x = cases.airfoil_x(s["nCells"])
+    assert np.array_equal(cases.digest(A.Amul(x)), g["sha_amul"])
+    psi = x.copy()
+    ldub200.lduMatrix.smoother.New("p", A, "GaussSeidel").smooth(psi, s["source"], 2)
+    assert np.array_equal(cases.digest(psi), g["sha_smooth_GaussSeidel"])
+    P = ldub200.lduMatrix.preconditioner.New(A, "DIC")
+    assert np.array_equal(cases.digest(P.precondition(s["source"])), g["sha_pre_DIC"])
+    for i, ctl in enumerate(cases.AIRFOIL_SOLVES):
+        ref = g[f"perf_{i}"]
+        psi = s["psi0"].copy()
+        perf = ldub200.lduMatrix.solver.New("p", A, dict(ctl, referenceOrderSums=True)).solve(psi, s["source"])
+        assert perf.nIterations == int(ref[2]), ctl
+        assert perf.initialResidual == ref[0] and perf.finalResidual == ref[1], ctl
+        assert np.array_equal(cases.digest(psi), g[f"sha_psi_{i}"]), ctl
+        psi = s["psi0"].copy()
+        perf = ldub200.lduMatrix.solver.New("p", A, ctl).solve(psi, s["source"])   # tree-ordered sums
+        assert abs(perf.nIterations - int(ref[2])) <= 1, ctl
+    A.destroy()

@@ -143,3 +143,18 @@ def test_plugin_multi_rank_with_cyclic_patches():
     assert perf_gpu["finalResidual"] == perf_ref["finalResidual"]
     for a, b in zip(psi_gpu, psi_ref):
         assert np.array_equal(a, b)
+
+
+def test_plugin_multi_rank_airfoil():
+    """the airFoil2D mesh cut into 3 regions: coupled reference ranks solving through the plug-in"""
+    import numpy as np
+    from ldub200 import decompose
+    s, _ = cases.airfoil_system()
+    regs = decompose.decompose(s, (np.arange(s["nCells"]) * 3 // s["nCells"]).astype(np.int32), 3)
+    ctl = dict(solver="PCG", preconditioner="DIC", tolerance=1e-7, relTol=0)
+    psi_ref, perf_ref = run_par(regs, ctl, plugin=False)
+    psi_gpu, perf_gpu = run_par(regs, dict(ctl, solver="gpuPCG", referenceOrderSums=True), plugin=True)
+    assert perf_gpu["nIterations"] == perf_ref["nIterations"]
+    assert perf_gpu["finalResidual"] == perf_ref["finalResidual"]
+    for a, b in zip(psi_gpu, psi_ref):
+        assert np.array_equal(a, b)
