@@ -591,33 +591,58 @@ struct Products {
     double* B[3];
 };
 
-__host__ __device__ inline long long tile_pos2(const Box2& b, int i, int j, int k)
+// Same CTA shape as pack2_kernel: one (k, 32-line column) tile x 32 steps per block, read in natural
+// cell order (lanes along i: coalesced), written in tile order (lanes along the line index:
+// coalesced) through shared memory.  HALF 0: the backward products B[0..2], HALF 1: the forward F[0..2].
+// (One thread per cell writing straight to its tile position spreads every warp's stores over 32
+// cache lines: 961 us on 216^3 for what is 0.9 GB of traffic.)
+template <int HALF>
+__global__ void __launch_bounds__(256) products2_kernel(Box2 b, int nBlk, const int* __restrict__ ownerStart,
+                                                         const double* __restrict__ rD,
+                                                         const double* __restrict__ coefF,
+                                                         const double* __restrict__ coefB, Products P)
 {
-    const int J = j >> 5, l = j & 31;
-    return ((long long)(k * b.nJ + J) * b.steps + (i + l)) * 32 + l;
-}
-
-__global__ void __launch_bounds__(kBlock) products2_kernel(Box2 b, const int* __restrict__ ownerStart,
-                                                           const double* __restrict__ rD,
-                                                           const double* __restrict__ coefF,
-                                                           const double* __restrict__ coefB, Products P)
-{
-    const int n = b.nx * b.ny * b.nz;
-    for (int c = blockIdx.x * kBlock + threadIdx.x; c < n; c += gridDim.x * kBlock) {
-        const int i = c % b.nx, j = (c / b.nx) % b.ny, k = c / (b.nx * b.ny);
-        const long long p = tile_pos2(b, i, j, k);
-        const int hasI = i < b.nx - 1, hasJ = j < b.ny - 1, hasK = k < b.nz - 1;
-        const int os = ownerStart[c];
-        const double r = rD[c];
-        // faces this cell owns, in the order +i, +j, +k
-        P.B[2][p] = hasI ? __dmul_rn(r, coefB[os]) : 0.0;
-        P.B[1][p] = hasJ ? __dmul_rn(r, coefB[os + hasI]) : 0.0;
-        P.B[0][p] = hasK ? __dmul_rn(r, coefB[os + hasI + hasJ]) : 0.0;
-        // faces where it is the upper cell: the +k / +j / +i face of the cell below /
-        // behind / to the left (those cells have the same i, j flags where it matters)
-        P.F[0][p] = k > 0 ? __dmul_rn(r, coefF[ownerStart[c - b.nx * b.ny] + hasI + hasJ]) : 0.0;
-        P.F[1][p] = j > 0 ? __dmul_rn(r, coefF[ownerStart[c - b.nx] + hasI]) : 0.0;
-        P.F[2][p] = i > 0 ? __dmul_rn(r, coefF[ownerStart[c - 1]]) : 0.0;
+    __shared__ double s[3][32][33];
+    const int T = blockIdx.x / nBlk, tb = (blockIdx.x - T * nBlk) * 32;
+    const int k = T / b.nJ, J = T - k * b.nJ;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = wid; r < 32; r += 8) {
+        const int j = J * 32 + r, i = tb - r + lane;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (j < b.ny && i >= 0 && i < b.nx) {
+            const int c = (k * b.ny + j) * b.nx + i;
+            const int hasI = i < b.nx - 1, hasJ = j < b.ny - 1, hasK = k < b.nz - 1;
+            const double rr = rD[c];
+            if (HALF == 0) {
+                // faces this cell owns, in the order +i, +j, +k
+                const int os = ownerStart[c];
+                v2 = hasI ? __dmul_rn(rr, coefB[os]) : 0.0;
+                v1 = hasJ ? __dmul_rn(rr, coefB[os + hasI]) : 0.0;
+                v0 = hasK ? __dmul_rn(rr, coefB[os + hasI + hasJ]) : 0.0;
+            } else {
+                // faces where it is the upper cell: the +k / +j / +i face of the cell below /
+                // behind / to the left (those cells have the same i, j flags where it matters)
+                v0 = k > 0 ? __dmul_rn(rr, coefF[ownerStart[c - b.nx * b.ny] + hasI + hasJ]) : 0.0;
+                v1 = j > 0 ? __dmul_rn(rr, coefF[ownerStart[c - b.nx] + hasI]) : 0.0;
+                v2 = i > 0 ? __dmul_rn(rr, coefF[ownerStart[c - 1]]) : 0.0;
+            }
+        }
+        s[0][r][lane] = v0;
+        s[1][r][lane] = v1;
+        s[2][r][lane] = v2;
+    }
+    __syncthreads();
+    double* const o0 = HALF == 0 ? P.B[0] : P.F[0];
+    double* const o1 = HALF == 0 ? P.B[1] : P.F[1];
+    double* const o2 = HALF == 0 ? P.B[2] : P.F[2];
+    for (int x = wid; x < 32; x += 8) {
+        const int t = tb + x;
+        if (t < b.steps) {
+            const long long p = ((long long)T * b.steps + t) * 32 + lane;
+            o0[p] = s[0][lane][x];
+            o1[p] = s[1][lane][x];
+            o2[p] = s[2][lane][x];
+        }
     }
 }
 
@@ -734,8 +759,14 @@ int products_for(ldu_matrix* m, State2* s, const double* rD, const double* coefF
         }
         ps.allocated = true;
     }
-    products2_kernel<<<grid_for(m->ctx, m->nCells), kBlock, 0, st>>>(s->b, m->d_ownerStart, rD, coefF, coefB, ps.P);
-    count_launch();
+    {
+        const int nBlk = (s->b.steps + 31) / 32;
+        const int grid = s->b.nTiles * nBlk;
+        products2_kernel<0><<<grid, 256, 0, st>>>(s->b, nBlk, m->d_ownerStart, rD, coefF, coefB, ps.P);
+        count_launch();
+        products2_kernel<1><<<grid, 256, 0, st>>>(s->b, nBlk, m->d_ownerStart, rD, coefF, coefB, ps.P);
+        count_launch();
+    }
     LDU_CUDA(cudaGetLastError());
     ps.rD = rD;
     ps.coefF = coefF;
