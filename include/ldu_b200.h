@@ -162,6 +162,10 @@ int ldu_matrix_destroy(ldu_matrix* m);
  * Coefficients, refreshed every solve (lduMatrix.H:77-86; lower == NULL means
  * symmetric: lduMatrix.C:198-215).  bouCoeffs/intCoeffs: one array per interface
  * (interfaceBouCoeffs_/interfaceIntCoeffs_, lduMatrix.H:97-104).  Host pointers.
+ * upper == NULL and lower == NULL (allowed only when nFaces == 0) is lduMatrix::diagonal()
+ * (lduMatrix.H:547-550): ldu_solve then runs diagonalSolver whatever the controls say
+ * (lduMatrixSolver.C:52-66).  A faceless matrix given a non-NULL upper is NOT diagonal() — the
+ * state fvm::laplacian leaves on a one-cell mesh — and goes to the selected solver.
  */
 int ldu_matrix_set_coeffs(ldu_matrix* m, const double* diag, const double* upper,
                           const double* lower, const double* const* bouCoeffs,

@@ -529,6 +529,7 @@ int ldu_matrix_set_coeffs(ldu_matrix* m, const double* diag, const double* upper
     }
     // the host arrays may be pageable and reused by the caller right away
     LDU_CUDA(cudaStreamSynchronize(st));
+    m->diagonalOnly = (upper == nullptr && lower == nullptr);
     m->haveCoeffs = true;
     m->coefGen++;
     return LDU_OK;
@@ -547,6 +548,7 @@ int ldu_matrix_set_coeffs_device(ldu_matrix* m, const double* d_diag, const doub
             LDU_CUDA(cudaMemcpyAsync(m->d_lower, d_lower, m->nFaces * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     m->coefGen++;
+    m->diagonalOnly = (d_upper == nullptr && d_lower == nullptr);
     m->haveCoeffs = true;
     return LDU_OK;
 }

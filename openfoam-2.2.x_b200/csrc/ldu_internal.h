@@ -136,6 +136,7 @@ struct ldu_matrix {
     int nCells = 0, nFaces = 0;
     bool symmetric = true;
     bool haveCoeffs = false;
+    bool diagonalOnly = false;     // lduMatrix::diagonal(): set_coeffs was given neither upper nor lower
     // addressing (device)
     int* d_l = nullptr;
     int* d_u = nullptr;

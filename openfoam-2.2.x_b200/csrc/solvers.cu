@@ -606,8 +606,10 @@ int solve_device(ldu_matrix* m, const ldu_controls* c, double* d_psi, const doub
     LDU_CUDA(cudaSetDevice(m->ctx->device));
     m->referenceOrderSums = (c->referenceOrderSums != 0);
     int rc;
-    // matrix.diagonal() -> diagonalSolver whatever the dictionary says (lduMatrixSolver.C:52-66)
-    if (c->solver == LDU_SOLVER_DIAGONAL || (m->nFaces == 0 && m->ctx->comm.nRanks == 1)) {
+    // matrix.diagonal() -> diagonalSolver whatever the dictionary says (lduMatrixSolver.C:52-66).
+    // diagonal() means "no upper and no lower field" (lduMatrix.H:547-550), not "no faces": a faceless
+    // mesh whose upper() exists (fvm::laplacian always touches it) goes to the selected solver
+    if (c->solver == LDU_SOLVER_DIAGONAL || (m->diagonalOnly && m->ctx->comm.nRanks == 1)) {
         rc = diagonal_solve(m, c, d_psi, d_source);
     } else {
         switch (c->solver) {

@@ -347,16 +347,22 @@ class lduMatrix:
 
     # -- coefficients --------------------------------------------------------------
     def set_coeffs(self, diag, upper, lower=None, bouCoeffs=(), intCoeffs=()):
-        diag, upper = _f64(diag), _f64(upper)
-        lower = None if lower is None else _f64(lower)
-        assert diag.size == self.nCells and upper.size == self.nFaces
+        """upper=None (only without faces): the matrix is lduMatrix::diagonal() and every solve goes to
+        diagonalSolver; an EMPTY upper array is a faceless matrix whose upper() exists."""
+        self._diagonal = upper is None and lower is None
+        diag = _f64(diag)
+        # a non-NULL pointer also for an empty array: NULL means "never set"
+        upper = None if upper is None else _f64(upper if np.size(upper) else np.zeros(1))
+        lower = None if lower is None else _f64(lower if np.size(lower) else np.zeros(1))
+        assert diag.size == self.nCells and (self.nFaces == 0 or upper.size == self.nFaces)
         n_if = len(self.interfaces)
         bou = [_f64(b) for b in bouCoeffs]
         inc = [_f64(b) for b in intCoeffs]
         assert len(bou) == n_if and len(inc) == n_if
         bp = (C.c_void_p * max(n_if, 1))(*[b.ctypes.data for b in bou])
         ip = (C.c_void_p * max(n_if, 1))(*[b.ctypes.data for b in inc])
-        _check(self.L.ldu_matrix_set_coeffs(self.h, diag.ctypes.data, upper.ctypes.data,
+        _check(self.L.ldu_matrix_set_coeffs(self.h, diag.ctypes.data,
+                                            None if upper is None else upper.ctypes.data,
                                             None if lower is None else lower.ctypes.data, bp, ip),
                "ldu_matrix_set_coeffs")
         self._symmetric = lower is None
@@ -473,7 +479,7 @@ class lduMatrix:
         def _name(self):
             d = self.controlDict
             s = d.get("solver", "PCG")
-            if self.matrix.nFaces == 0 and self.matrix.ctx.nRanks == 1:
+            if getattr(self.matrix, "_diagonal", False) and self.matrix.ctx.nRanks == 1:
                 return "diagonal"
             if s in ("PCG", "PBiCG"):   # preconditioner name + typeName (PCG.C:72-77)
                 pre = d.get("preconditioner", "none")

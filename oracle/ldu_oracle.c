@@ -68,6 +68,7 @@ struct orc_world {
     const double** faceWeights;
     orc_hierarchy* h;         /* [R] or NULL */
     int hBuilt;
+    int diagonalOnly;         /* lduMatrix::diagonal(): no upper and no lower coefficients were ever set */
 };
 
 /* lduMatrix::H: LM/lduMatrix/lduMatrixTemplates.C:33-65 (off-diagonal product, negated;
@@ -185,6 +186,11 @@ static void hierarchy_clear(orc_hierarchy* h)
     }
     memset(h, 0, sizeof(*h));
 }
+
+/* lduMatrix::diagonal() (lduMatrix.H:547-550) is about which coefficient fields EXIST, not about the
+ * number of faces: a mesh without internal faces whose upper() was touched (fvm::laplacian always
+ * does) is not "diagonal" and goes to the selected solver */
+void orc_world_set_diagonal(orc_world* w, int flag) { w->diagonalOnly = flag; }
 
 orc_world* orc_world_new(int nRegions)
 {
@@ -1642,13 +1648,9 @@ int orc_solve(orc_world* w, const orc_controls* c, double** psi, double** source
 {
     w->hBuilt = 0;
     /* matrix.diagonal() -> diagonalSolver unconditionally (lduMatrixSolver.C:52-66) */
-    {
-        int r, any = 0;
-        for (r = 0; r < w->R; r++) if (w->m[r].nFaces > 0) any = 1;
-        if (!any || c->solver == ORC_SOLVER_DIAGONAL) {
-            diagonal_solve(w->m, w->R, psi, source, perf);
-            return 0;
-        }
+    if (w->diagonalOnly || c->solver == ORC_SOLVER_DIAGONAL) {
+        diagonal_solve(w->m, w->R, psi, source, perf);
+        return 0;
     }
     switch (c->solver) {
     case ORC_SOLVER_PCG:

@@ -69,6 +69,7 @@ def lib():
         L.orc_world_add_interface.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3
         L.orc_world_add_interface.restype = C.c_int
         L.orc_world_set_face_weights.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_world_set_diagonal.argtypes = [C.c_void_p, C.c_int]
         for name in ("orc_amul", "orc_tmul", "orc_H", "orc_faceH"):
             getattr(L, name).argtypes = [C.c_void_p, PP, PP]
         L.orc_sumA.argtypes = [C.c_void_p, PP]
@@ -164,7 +165,7 @@ class World:
             lo = np.ascontiguousarray(reg["lower"], dtype=np.int32)
             up = np.ascontiguousarray(reg["upper"], dtype=np.int32)
             diag = _f64(reg["diag"])
-            uc = _f64(reg["upperCoef"])
+            uc = _f64(np.zeros(0) if reg["upperCoef"] is None else reg["upperCoef"])
             lc = None if reg.get("lowerCoef") is None else _f64(reg["lowerCoef"])
             self._keep += [lo, up, diag, uc, lc]
             self.nCells.append(diag.size)
@@ -176,6 +177,9 @@ class World:
                 fw = _f64(reg["faceWeights"])
                 self._keep.append(fw)
                 L.orc_world_set_face_weights(self.w, r, fw.ctypes.data)
+        # lduMatrix::diagonal(): upper and lower were never set (only possible without faces)
+        L.orc_world_set_diagonal(self.w, int(all(reg["upperCoef"] is None and reg.get("lowerCoef") is None
+                                                 for reg in regions)))
         for r, reg in enumerate(regions):
             for it in reg.get("interfaces", []):
                 fc = np.ascontiguousarray(it["faceCells"], dtype=np.int32)
@@ -330,12 +334,13 @@ def _write_problem(path, sysd, psi=None, source=None):
     weights = sysd.get("faceWeights") is not None
     n = np.asarray(sysd["diag"]).size
     with open(path, "wb") as fh:
-        np.array([0x3155444C, n, np.asarray(sysd["lower"]).size, int(asym), int(weights)],
+        diagonal = sysd["upperCoef"] is None
+        np.array([0x3155444C, n, np.asarray(sysd["lower"]).size, int(asym), int(weights) | (2 if diagonal else 0)],
                  dtype=np.int32).tofile(fh)
         np.asarray(sysd["lower"], dtype=np.int32).tofile(fh)
         np.asarray(sysd["upper"], dtype=np.int32).tofile(fh)
         _f64(sysd["diag"]).tofile(fh)
-        _f64(sysd["upperCoef"]).tofile(fh)
+        _f64(np.zeros(0) if diagonal else sysd["upperCoef"]).tofile(fh)
         if asym:
             _f64(sysd["lowerCoef"]).tofile(fh)
         _f64(sysd["source"] if source is None else source).tofile(fh)

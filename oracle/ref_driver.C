@@ -23,7 +23,8 @@
   operation (the `libs` entry of a case's controlDict), so a dictionary may select a plug-in.
 
   Problem file (little endian):
-      int32 magic(0x3155444c 'LDU1') nCells nFaces asym hasWeights
+      int32 magic(0x3155444c 'LDU1') nCells nFaces asym flags(1: face weights, 2: diagonal matrix,
+                                                              upper() never touched)
       int32 lower[nFaces] upper[nFaces]
       f64   diag[nCells] upper[nFaces] (lower[nFaces] if asym)
       f64   source[nCells] psi0[nCells] (faceWeights[nFaces] if hasWeights)
@@ -473,7 +474,8 @@ int main(int argc, char* argv[])
     const label nCells = hdr[1];
     const label nFaces = hdr[2];
     const bool asym = hdr[3];
-    const bool hasWeights = hdr[4];
+    const bool hasWeights = hdr[4] & 1;
+    const bool diagonalOnly = hdr[4] & 2;    // leave upper/lower unallocated: lduMatrix::diagonal()
 
     labelList l(nFaces), u(nFaces);
     readOrDie(l.begin(), sizeof(label), nFaces, f);
@@ -553,7 +555,7 @@ int main(int argc, char* argv[])
 
     lduMatrix A(mesh);
     A.diag() = diag;
-    A.upper() = upper;
+    if (!diagonalOnly) A.upper() = upper;
     if (asym) A.lower() = lower;
 
     scalarField out(nCells, 0.0);

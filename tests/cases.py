@@ -149,6 +149,57 @@ CYCLIC_REGION_SOLVES = [
 ]
 
 
+# edge cases of the solver front end (lduMatrixSolver.C:40-136, PCG.C:84-181): (system, controls,
+# initial guess, source).  Systems "faceless6" / "diagonal6": six cells without faces, the first with an
+# (empty) upper field as fvm::laplacian leaves it -> the selected solver runs; the second without upper
+# and lower -> lduMatrix::diagonal() -> diagonalSolver whatever the dictionary says.
+_PCG = dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0)
+_BICG = dict(solver="PBiCG", preconditioner="DILU", tolerance=1e-8, relTol=0)
+EDGE_SOLVES = [
+    ("faceless6", _PCG, "zero", "given"),
+    ("faceless6", dict(solver="smoothSolver", smoother="GaussSeidel", tolerance=1e-8, relTol=0), "zero", "given"),
+    ("diagonal6", _PCG, "zero", "given"),
+    ("diagonal6", dict(_GAMG, agglomerator="algebraicPair", tolerance=1e-8, relTol=0), "random", "given"),
+    ("single", _PCG, "random", "given"),
+    ("box12_var", dict(_PCG, maxIter=0), "zero", "given"),          # the loop body still runs once
+    ("box12_var", dict(_PCG, maxIter=1), "zero", "given"),
+    ("box12_var", _PCG, "random", "given"),
+    ("box12_var", _PCG, "exact", "given"),                          # converged before the first iteration
+    ("box12_var", _PCG, "zero", "zero"),                            # normFactor = 1e-20 only
+    ("box12_var", _PCG, "random", "zero"),
+    ("box12_var", dict(solver="PCG", preconditioner="DIC", tolerance=0, relTol=0.05), "zero", "given"),
+    ("box12_var", dict(solver="PCG", preconditioner="DIC", tolerance=10.0, relTol=0), "zero", "given"),
+    ("box12_var", dict(solver="smoothSolver", smoother="GaussSeidel", nSweeps=5, tolerance=1e-12, relTol=0,
+                       maxIter=7), "zero", "given"),                # nSweeps does not divide maxIter
+    ("box12_var", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0, maxIter=0), "zero", "given"),
+    ("asym10", _BICG, "random", "given"),
+    ("asym10", _BICG, "zero", "zero"),
+    ("asym10", dict(_BICG, maxIter=1), "zero", "given"),
+]
+
+
+def edge_case(i):
+    """-> (system dict, controls, psi0, source) of EDGE_SOLVES[i]"""
+    name, ctl, guess, src = EDGE_SOLVES[i]
+    if name in ("faceless6", "diagonal6"):
+        n = 6
+        s = dict(nCells=n, nFaces=0, lower=np.zeros(0, np.int32), upper=np.zeros(0, np.int32),
+                 diag=-(1.0 + np.arange(n)), upperCoef=np.zeros(0) if name == "faceless6" else None,
+                 lowerCoef=None, source=np.sin(np.arange(n) + 1.0), psi0=np.zeros(n), faceWeights=None)
+    else:
+        s = system(name)
+    rng = np.random.default_rng(100 + i)
+    source = np.zeros(s["nCells"]) if src == "zero" else s["source"]
+    if guess == "random":
+        psi0 = rng.standard_normal(s["nCells"])
+    elif guess == "exact":
+        from oracle import oracle as O
+        psi0 = O.World([s]).solve(dict(ctl, tolerance=1e-14), s["psi0"].copy(), source)[0][0]
+    else:
+        psi0 = np.zeros(s["nCells"])
+    return s, ctl, psi0, source
+
+
 # a real unstructured mesh: the polyMesh shipped with the reference's airFoil2D tutorial (10,720 cells,
 # 21,254 internal faces), read by ldub200.polymesh; tests/golden/airfoil2d.npz carries the system built
 # from it and the reference's results, so the tests run where /root/reference is absent

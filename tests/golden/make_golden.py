@@ -109,6 +109,17 @@ def main():
                                      perf["nIterations"], perf["converged"], perf["singular"]], dtype=np.float64)
         print("cyclic solve", i, name, ctl["solver"], perf["nIterations"])
     np.savez_compressed(HERE / "cyclic.npz", **cyc)
+    # edge cases of the solver front end
+    edge = {}
+    for i in range(len(cases.EDGE_SOLVES)):
+        s, ctl, psi0, source = cases.edge_case(i)
+        psi, so = O.ref_run(s, "solve", O.dict_text(cases.ref_controls(ctl)), psi=psi0, source=source)
+        perf = O.parse_perf(so)
+        edge[f"psi_{i}"] = psi
+        edge[f"perf_{i}"] = np.array([perf["initialResidual"], perf["finalResidual"],
+                                      perf["nIterations"], perf["converged"], perf["singular"]], dtype=np.float64)
+        print("edge", i, cases.EDGE_SOLVES[i][0], perf["solverName"], perf["nIterations"])
+    np.savez_compressed(HERE / "edge_cases.npz", **edge)
     # a real unstructured mesh: the polyMesh the reference ships with the airFoil2D tutorial, read by
     # ldub200.polymesh; Laplacian coefficients from its geometry; solved by the reference
     from ldub200 import polymesh

@@ -374,3 +374,24 @@ def test_airfoil_real_unstructured_mesh(ctx):
         perf = ldub200.lduMatrix.solver.New("p", A, ctl).solve(psi, s["source"])   # tree-ordered sums
         assert abs(perf.nIterations - int(ref[2])) <= 1, ctl
     A.destroy()
+
+
+@pytest.mark.parametrize("case", range(len(cases.EDGE_SOLVES)))
+def test_edge_cases_bit_exact(ctx, case):
+    """solver front end corner cases against the REFERENCE's committed results (tests/golden/edge_cases.npz):
+    diagonal() vs faceless matrices, maxIter 0 and 1, converged / random initial guesses, zero sources"""
+    import ldub200
+    g = np.load(cases.__file__.replace("cases.py", "golden/edge_cases.npz"))
+    s, ctl, psi0, source = cases.edge_case(case)
+    A = ldub200.lduMatrix(ctx, s["nCells"], s["lower"], s["upper"])
+    A.set_coeffs(s["diag"], s["upperCoef"], s["lowerCoef"])
+    if s.get("faceWeights") is not None:
+        A.set_face_weights(s["faceWeights"])
+    psi = psi0.copy()
+    perf = ldub200.lduMatrix.solver.New("p", A, dict(ctl, referenceOrderSums=True)).solve(psi, source)
+    ref = g[f"perf_{case}"]
+    assert perf.nIterations == int(ref[2]), (str(perf), ref)
+    assert perf.initialResidual == ref[0] and perf.finalResidual == ref[1], (str(perf), ref)
+    assert perf.converged == bool(ref[3]) and perf.singular == bool(ref[4])
+    assert np.array_equal(psi, g[f"psi_{case}"])
+    A.destroy()

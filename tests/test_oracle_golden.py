@@ -154,3 +154,17 @@ def test_cyclic_solves(case):
     assert perf["finalResidual"] == ref[1]
     assert perf["nIterations"] == int(ref[2])
     assert np.array_equal(psi[0], g[f"psi_{case}"])
+
+
+# --- edge cases of the solver front end (diagonal / faceless matrices, maxIter 0/1, initial guesses,
+# --- zero sources, tolerance corner cases)
+@pytest.mark.parametrize("case", range(len(cases.EDGE_SOLVES)))
+def test_edge_cases(case):
+    g = np.load(GOLD / "edge_cases.npz")
+    s, ctl, psi0, source = cases.edge_case(case)
+    psi, perf = O.World([s]).solve(ctl, psi0.copy(), source)
+    ref = g[f"perf_{case}"]
+    assert perf["initialResidual"] == ref[0] and perf["finalResidual"] == ref[1]
+    assert perf["nIterations"] == int(ref[2])
+    assert perf["converged"] == bool(ref[3]) and perf["singular"] == bool(ref[4])
+    assert np.array_equal(psi[0], g[f"psi_{case}"])

@@ -105,3 +105,29 @@ def test_cyclic_solves(case):
     assert perf_o["initialResidual"] == perf_r["initialResidual"]
     assert perf_o["finalResidual"] == perf_r["finalResidual"]
     assert np.array_equal(psi_o[0], psi_r)
+
+
+# --- edge cases of the solver front end: diagonal / faceless matrices, maxIter 0 and 1, converged or
+# --- random initial guesses, zero sources, relTol-only and huge tolerances
+@pytest.mark.parametrize("case", range(len(cases.EDGE_SOLVES)))
+def test_edge_cases(case):
+    s, ctl, psi0, source = cases.edge_case(case)
+    psi_o, perf_o = O.World([s]).solve(ctl, psi0.copy(), source)
+    psi_r, so = O.ref_run(s, "solve", O.dict_text(cases.ref_controls(ctl)), psi=psi0, source=source)
+    perf_r = O.parse_perf(so)
+    for key in ("initialResidual", "finalResidual", "nIterations", "converged", "singular"):
+        assert perf_o[key] == perf_r[key], (key, perf_o, perf_r)
+    assert np.array_equal(psi_o[0], psi_r)
+    if cases.EDGE_SOLVES[case][0] == "diagonal6":
+        assert perf_r["solverName"] == "diagonal"
+
+
+def test_gamg_without_coarse_levels_is_an_error():
+    """GAMGSolver.C:108-126: the reference stops with "No coarse levels created"; so does the oracle"""
+    s = cases.system("line50")
+    ctl = dict(solver="GAMG", smoother="GaussSeidel", agglomerator="algebraicPair", nCellsInCoarsestLevel=100,
+               mergeLevels=1, tolerance=1e-8, relTol=0)
+    with pytest.raises(AssertionError):
+        O.World([s]).solve(ctl, s["psi0"], s["source"])
+    with pytest.raises(RuntimeError, match="No coarse levels created"):
+        O.ref_run(s, "solve", O.dict_text(ctl))
