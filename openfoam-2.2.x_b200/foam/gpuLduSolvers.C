@@ -22,12 +22,16 @@ namespace Foam
 {
     defineTypeNameAndDebug(gpuPCG, 0);
     defineTypeNameAndDebug(gpuPBiCG, 0);
+    defineTypeNameAndDebug(gpuICCG, 0);
+    defineTypeNameAndDebug(gpuBICCG, 0);
     defineTypeNameAndDebug(gpuSmoothSolver, 0);
     defineTypeNameAndDebug(gpuGAMG, 0);
 
     // symmetric matrices: PCG, GAMG, smoothSolver (PCG.C:34, GAMGSolver.C:34, smoothSolver.C:34)
     lduMatrix::solver::addsymMatrixConstructorToTable<gpuPCG>
         addgpuPCGSymMatrixConstructorToTable_;
+    lduMatrix::solver::addsymMatrixConstructorToTable<gpuICCG>
+        addgpuICCGSymMatrixConstructorToTable_;
     lduMatrix::solver::addsymMatrixConstructorToTable<gpuGAMG>
         addgpuGAMGSymMatrixConstructorToTable_;
     lduMatrix::solver::addsymMatrixConstructorToTable<gpuSmoothSolver>
@@ -36,6 +40,8 @@ namespace Foam
     // asymmetric matrices: PBiCG, GAMG, smoothSolver (PBiCG.C:34, GAMGSolver.C:37, smoothSolver.C:37)
     lduMatrix::solver::addasymMatrixConstructorToTable<gpuPBiCG>
         addgpuPBiCGAsymMatrixConstructorToTable_;
+    lduMatrix::solver::addasymMatrixConstructorToTable<gpuBICCG>
+        addgpuBICCGAsymMatrixConstructorToTable_;
     lduMatrix::solver::addasymMatrixConstructorToTable<gpuGAMG>
         addgpuGAMGAsymMatrixConstructorToTable_;
     lduMatrix::solver::addasymMatrixConstructorToTable<gpuSmoothSolver>
@@ -58,6 +64,10 @@ namespace Foam
             );
             S::symMatrixConstructorTablePtr_->set
             (
+                "ICCG", S::addsymMatrixConstructorToTable<gpuICCG>::New
+            );
+            S::symMatrixConstructorTablePtr_->set
+            (
                 "GAMG", S::addsymMatrixConstructorToTable<gpuGAMG>::New
             );
             S::symMatrixConstructorTablePtr_->set
@@ -68,6 +78,10 @@ namespace Foam
             S::asymMatrixConstructorTablePtr_->set
             (
                 "PBiCG", S::addasymMatrixConstructorToTable<gpuPBiCG>::New
+            );
+            S::asymMatrixConstructorTablePtr_->set
+            (
+                "BICCG", S::addasymMatrixConstructorToTable<gpuBICCG>::New
             );
             S::asymMatrixConstructorTablePtr_->set
             (

@@ -136,10 +136,14 @@ def make_controls(d: dict) -> Controls:
     c = Controls()
     L.ldu_controls_default(C.byref(c))
     name = d.get("solver", "PCG")
-    if name in ("ICCG", "BICCG"):   # ICCG.C:40-54 / BICCG.C: PCG+DIC and PBiCG+DILU by name
-        d = dict(d, solver="PCG" if name == "ICCG" else "PBiCG",
-                 preconditioner="DIC" if name == "ICCG" else "DILU")
+    if name in ("ICCG", "BICCG"):
+        # the table constructors of ICCG / BICCG hand the dictionary to PCG / PBiCG unchanged
+        # (ICCG.C:67-86, BICCG.C:67-86): same solver, the dictionary's own preconditioner
+        d = dict(d, solver="PCG" if name == "ICCG" else "PBiCG")
         name = d["solver"]
+    if "solver" in d and name in ("PCG", "PBiCG") and "preconditioner" not in d:
+        # lduMatrixPreconditioner.C:39-58 looks the entry up without a default
+        raise LduError("keyword preconditioner is undefined in the solver dictionary")
     if name not in SOLVERS:
         # lduMatrixSolver.C:96-110: unknown solver is a FatalIOError listing the table
         raise LduError(f"Unknown solver {name}; valid solvers are {sorted(SOLVERS)}")
@@ -481,6 +485,7 @@ class lduMatrix:
             s = d.get("solver", "PCG")
             if getattr(self.matrix, "_diagonal", False) and self.matrix.ctx.nRanks == 1:
                 return "diagonal"
+            s = {"ICCG": "PCG", "BICCG": "PBiCG"}.get(s, s)
             if s in ("PCG", "PBiCG"):   # preconditioner name + typeName (PCG.C:72-77)
                 pre = d.get("preconditioner", "none")
                 if isinstance(pre, dict):

@@ -105,7 +105,8 @@ def make_controls(d: dict) -> Controls:
     """OpenFOAM-style solver dictionary -> Controls (defaults as in the reference:
     lduMatrixSolver.C:164-169, smoothSolver.C:70-74, GAMGSolver.C:66-76,157-181)."""
     c = Controls()
-    c.solver = SOLVERS[d.get("solver", "PCG")]
+    # ICCG / BICCG selected at run time are PCG / PBiCG on the same dictionary (ICCG.C:67-86)
+    c.solver = SOLVERS[{"ICCG": "PCG", "BICCG": "PBiCG"}.get(d.get("solver", "PCG"), d.get("solver", "PCG"))]
     pre = d.get("preconditioner", "none")
     sub = {}
     if isinstance(pre, dict):

@@ -61,7 +61,7 @@ def test_dictionary_translation():
     assert c.smoother == api.SMOOTHERS["DIC"] and c.nVcycles == 3 and c.mergeLevels == 2
     assert c.precTolerance == 1e-5 and c.precRelTol == 0.1 and c.tolerance == 1e-9
     assert c.useFaceWeights == 0
-    c = ldub200.make_controls(dict(solver="ICCG"))      # ICCG.C: PCG + DIC
+    c = ldub200.make_controls(dict(solver="ICCG", preconditioner="DIC"))      # ICCG.C:67-86: PCG on the same dictionary
     assert c.solver == api.SOLVERS["PCG"] and c.preconditioner == api.PRECONDITIONERS["DIC"]
     with pytest.raises(ldub200.LduError):
         ldub200.make_controls(dict(solver="notASolver"))
@@ -84,3 +84,16 @@ def test_solver_performance_print_format():
     assert str(p) == "DICPCG:  Solving for p, Initial residual = 1, Final residual = 3.26718e-07, No Iterations 32"
     p = ldub200.SolverPerformance("DICPCG", "p", singular=True)
     assert str(p) == "DICPCG:  Solving for p:  solution singularity"
+
+
+def test_iccg_biccg_aliases_and_mandatory_preconditioner():
+    """ICCG / BICCG = PCG / PBiCG on the same dictionary (ICCG.C:67-86); the preconditioner entry has
+    no default (lduMatrixPreconditioner.C:39-58)"""
+    import ldub200
+    c = ldub200.make_controls(dict(solver="ICCG", preconditioner="diagonal", tolerance=1e-8))
+    assert c.solver == 0 and c.preconditioner == ldub200.api.PRECONDITIONERS["diagonal"]
+    c = ldub200.make_controls(dict(solver="BICCG", preconditioner="DILU"))
+    assert c.solver == 1 and c.preconditioner == ldub200.api.PRECONDITIONERS["DILU"]
+    for name in ("PCG", "PBiCG", "ICCG", "BICCG"):
+        with pytest.raises(ldub200.LduError, match="preconditioner"):
+            ldub200.make_controls(dict(solver=name, tolerance=1e-8))

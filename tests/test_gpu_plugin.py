@@ -158,3 +158,19 @@ def test_plugin_multi_rank_airfoil():
     assert perf_gpu["finalResidual"] == perf_ref["finalResidual"]
     for a, b in zip(psi_gpu, psi_ref):
         assert np.array_equal(a, b)
+
+
+def test_plugin_iccg_alias():
+    """`solver gpuICCG; preconditioner diagonal;` behaves like the reference's `solver ICCG; ...`"""
+    import numpy as np
+    if not (PLUGIN.exists() and O.ref_available()):
+        pytest.skip("plug-in / reference binaries not built")
+    s = cases.system("box12_var")
+    ctl = dict(solver="ICCG", preconditioner="diagonal", tolerance=1e-8, relTol=0)
+    psi_ref, so = O.ref_run(s, "solve", O.dict_text(ctl))
+    psi_gpu, so_gpu = O.ref_run(s, "solve", O.dict_text(dict(ctl, solver="gpuICCG", referenceOrderSums=True)),
+                                extra_env=dict(LDU_REF_LIBS=str(PLUGIN)))
+    a, b = O.parse_perf(so_gpu), O.parse_perf(so)
+    assert a["solverName"] == b["solverName"] == "diagonalPCG"
+    assert a["nIterations"] == b["nIterations"] and a["finalResidual"] == b["finalResidual"]
+    assert np.array_equal(psi_gpu, psi_ref)

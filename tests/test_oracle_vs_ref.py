@@ -131,3 +131,21 @@ def test_gamg_without_coarse_levels_is_an_error():
         O.World([s]).solve(ctl, s["psi0"], s["source"])
     with pytest.raises(RuntimeError, match="No coarse levels created"):
         O.ref_run(s, "solve", O.dict_text(ctl))
+
+
+@pytest.mark.parametrize("name,ctl", [
+    ("box12_var", dict(solver="ICCG", preconditioner="diagonal", tolerance=1e-8, relTol=0)),
+    ("box12_var", dict(solver="ICCG", preconditioner="DIC", tolerance=1e-8, relTol=0)),
+    ("asym10", dict(solver="BICCG", preconditioner="diagonal", tolerance=1e-8, relTol=0)),
+])
+def test_iccg_biccg_are_aliases(name, ctl):
+    """selected at run time, ICCG / BICCG pass the dictionary on to PCG / PBiCG (ICCG.C:67-86): the
+    dictionary's own preconditioner is used, and the performance line says <preconditioner>PCG"""
+    s = cases.system(name)
+    psi_o, perf_o = O.World([s]).solve(ctl, s["psi0"], s["source"])
+    psi_r, perf_r = O.ref_solve(s, ctl)
+    assert perf_r["solverName"] == ctl["preconditioner"] + ("PCG" if ctl["solver"] == "ICCG" else "PBiCG")
+    assert perf_o["nIterations"] == perf_r["nIterations"] and perf_o["finalResidual"] == perf_r["finalResidual"]
+    assert np.array_equal(psi_o[0], psi_r)
+    with pytest.raises(RuntimeError, match="keyword preconditioner is undefined"):
+        O.ref_solve(s, {k: v for k, v in ctl.items() if k != "preconditioner"})
