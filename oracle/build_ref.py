@@ -15,7 +15,7 @@ libraries the lduMatrix path needs:
   src/Pstream/dummy/Make/files     (serial Pstream stubs)
 
 and, for multi-rank runs of the reference without MPI (absent in this image),
-  oracle/_ref/libPstream_shm.so    oracle/pstream_shm/*.C: the Pstream seam over shared
+  oracle/_ref/libPstream_shm.so    oracle/pstream_shm/shmPstream.C: the Pstream seam over shared
                                    memory.  Like the reference's own libPstream (dummy vs mpi,
                                    picked by LD_LIBRARY_PATH) it interposes on the stubs:
                                    ref_driver_par lists it before libOpenFOAM.so, which stays
@@ -207,8 +207,7 @@ def build_driver(ln: Path):
         return r.returncode
     # the shared-memory Pstream and the multi-rank driver: same source, the seam listed first
     shm = HERE / "pstream_shm"
-    cmd = (f"{CXX} {CXXFLAGS} -shared -I{shm} -I{ln} {shm / 'UPstream.C'} {shm / 'UIPread.C'} "
-           f"{shm / 'UOPwrite.C'} -o {OUT / 'libPstream_shm.so'}")
+    cmd = f"{CXX} {CXXFLAGS} -shared -I{shm} -I{ln} {shm / 'shmPstream.C'} -o {OUT / 'libPstream_shm.so'}"
     r = subprocess.run(cmd.split())
     print(f"[build_ref] libPstream_shm.so -> exit {r.returncode}")
     if r.returncode:

@@ -5,6 +5,10 @@
 // Rank, size and the path of the mapped file come from the environment (set by oracle/oracle.py).
 // Scalar reductions sum in rank order, so every rank gets the bit-identical result.
 #include "UPstream.H"
+#include "UIPstream.H"
+#include "UOPstream.H"
+#include "PstreamBuffers.H"
+#include "error.H"
 #include "PstreamReduceOps.H"
 #include "shmWorld.H"
 
@@ -342,4 +346,91 @@ bool Foam::UPstream::finishedRequest(const label i)
 }
 
 
-// ************************************************************************* //
+// ---------------------------------------------------------------------------
+// UOPstream::write (what src/Pstream/mpi/UOPwrite.C does with MPI_Bsend/Send/Isend): every write is
+// buffered in the ring of the (this rank -> toProcNo) pair and complete on return, whatever the
+// commsType
+// ---------------------------------------------------------------------------
+bool Foam::UOPstream::write
+(
+    const commsTypes commsType,
+    const int toProcNo,
+    const char* buf,
+    const std::streamsize bufSize,
+    const int tag
+)
+{
+    lduShm::sendBytes(toProcNo, buf, bufSize, tag);
+    return true;
+}
+
+
+// ---------------------------------------------------------------------------
+// UIPstream (src/Pstream/mpi/UIPread.C).  Only the contiguous-data read is provided — it is what the
+// lduMatrix path uses (processorLduInterface::send/receive, Pstream::gather/scatter of contiguous
+// types); the token-stream constructors stop with an error.
+// ---------------------------------------------------------------------------
+static void noTokenStreams()
+{
+    FatalErrorIn("UIPstream::UIPstream")
+        << "the shared-memory Pstream of the lduMatrix test harness carries contiguous data only"
+        << Foam::abort(Foam::FatalError);
+}
+
+Foam::UIPstream::UIPstream
+(
+    const commsTypes commsType,
+    const int fromProcNo,
+    DynamicList<char>& externalBuf,
+    label& externalBufPosition,
+    const int tag,
+    const bool clearAtEnd,
+    streamFormat format,
+    versionNumber version
+)
+:
+    UPstream(commsType),
+    Istream(format, version),
+    fromProcNo_(fromProcNo),
+    externalBuf_(externalBuf),
+    externalBufPosition_(externalBufPosition),
+    tag_(tag),
+    clearAtEnd_(clearAtEnd),
+    messageSize_(0)
+{
+    noTokenStreams();
+}
+
+Foam::UIPstream::UIPstream(const int fromProcNo, PstreamBuffers& buffers)
+:
+    UPstream(buffers.commsType_),
+    Istream(buffers.format_, buffers.version_),
+    fromProcNo_(fromProcNo),
+    externalBuf_(buffers.recvBuf_[fromProcNo]),
+    externalBufPosition_(buffers.recvBufPos_[fromProcNo]),
+    tag_(buffers.tag_),
+    clearAtEnd_(true),
+    messageSize_(0)
+{
+    noTokenStreams();
+}
+
+Foam::label Foam::UIPstream::read
+(
+    const commsTypes commsType,
+    const int fromProcNo,
+    char* buf,
+    const std::streamsize bufSize,
+    const int tag
+)
+{
+    if (commsType == nonBlocking)
+    {
+        lduShm::postRecv(fromProcNo, buf, bufSize, tag);   // completed by UPstream::waitRequests
+    }
+    else
+    {
+        lduShm::recvBytes(fromProcNo, buf, bufSize, tag);
+    }
+    return bufSize;
+}

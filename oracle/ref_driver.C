@@ -454,7 +454,7 @@ int main(int argc, char* argv[])
     const bool parallel = getenv("LDU_PSTREAM_SIZE") != NULL;
     if (parallel)
     {
-        UPstream::init(argc, argv);     // oracle/pstream_shm/UPstream.C
+        UPstream::init(argc, argv);     // oracle/pstream_shm/shmPstream.C
     }
     char probFile[4096], outFile[4096];
     snprintf(probFile, sizeof(probFile), argv[1], int(Pstream::myProcNo()));
