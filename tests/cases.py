@@ -178,6 +178,24 @@ EDGE_SOLVES = [
 ]
 
 
+# singular systems (SolverPerformance::checkSingularity, SolverPerformance.C:31-52): an all-zero matrix
+# makes wApA vanish in the first iteration -> singular, not converged, no iteration counted
+SINGULAR_SOLVES = [
+    ("box12_var", dict(solver="PCG", preconditioner="none", tolerance=1e-8, relTol=0)),
+    ("asym10", dict(solver="PBiCG", preconditioner="none", tolerance=1e-8, relTol=0)),
+]
+
+
+def singular_case(i):
+    name, ctl = SINGULAR_SOLVES[i]
+    s = dict(system(name))
+    s["diag"] = np.zeros_like(s["diag"])
+    s["upperCoef"] = np.zeros_like(s["upperCoef"])
+    if s["lowerCoef"] is not None:
+        s["lowerCoef"] = np.zeros_like(s["lowerCoef"])
+    return s, ctl
+
+
 def edge_case(i):
     """-> (system dict, controls, psi0, source) of EDGE_SOLVES[i]"""
     name, ctl, guess, src = EDGE_SOLVES[i]

@@ -395,3 +395,21 @@ def test_edge_cases_bit_exact(ctx, case):
     assert perf.converged == bool(ref[3]) and perf.singular == bool(ref[4])
     assert np.array_equal(psi, g[f"psi_{case}"])
     A.destroy()
+
+
+@pytest.mark.parametrize("case", range(len(cases.SINGULAR_SOLVES)))
+def test_singular_matrix(ctx, case):
+    """SolverPerformance::checkSingularity: an all-zero matrix -> singular, 0 iterations, psi untouched,
+    and the reference's "solution singularity" print"""
+    import ldub200
+    s, ctl = cases.singular_case(case)
+    O = _oracle()
+    psi_o, perf_o = O.World([s]).solve(ctl, s["psi0"].copy(), s["source"])
+    A = _matrix(ctx, s)
+    psi = s["psi0"].copy()
+    perf = ldub200.lduMatrix.solver.New("p", A, ctl).solve(psi, s["source"])
+    assert perf.singular and not perf.converged and perf.nIterations == perf_o["nIterations"] == 0
+    assert perf.initialResidual == perf_o["initialResidual"] and perf.finalResidual == perf_o["finalResidual"]
+    assert np.array_equal(psi, psi_o[0])
+    assert str(perf).endswith("solution singularity")
+    A.destroy()

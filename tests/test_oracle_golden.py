@@ -168,3 +168,14 @@ def test_edge_cases(case):
     assert perf["nIterations"] == int(ref[2])
     assert perf["converged"] == bool(ref[3]) and perf["singular"] == bool(ref[4])
     assert np.array_equal(psi[0], g[f"psi_{case}"])
+
+
+@pytest.mark.parametrize("case", range(len(cases.SINGULAR_SOLVES)))
+def test_singular_matrix(case):
+    """the reference's answer (oracle/_ref run recorded in test_oracle_vs_ref.py::test_singular_matrix):
+    singular, not converged, 0 iterations, residuals 1, psi untouched"""
+    s, ctl = cases.singular_case(case)
+    psi, perf = O.World([s]).solve(ctl, s["psi0"].copy(), s["source"])
+    assert perf["singular"] and not perf["converged"] and perf["nIterations"] == 0
+    assert perf["initialResidual"] == 1.0 and perf["finalResidual"] == 1.0
+    assert np.array_equal(psi[0], s["psi0"])

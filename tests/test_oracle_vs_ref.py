@@ -149,3 +149,14 @@ def test_iccg_biccg_are_aliases(name, ctl):
     assert np.array_equal(psi_o[0], psi_r)
     with pytest.raises(RuntimeError, match="keyword preconditioner is undefined"):
         O.ref_solve(s, {k: v for k, v in ctl.items() if k != "preconditioner"})
+
+
+@pytest.mark.parametrize("case", range(len(cases.SINGULAR_SOLVES)))
+def test_singular_matrix(case):
+    s, ctl = cases.singular_case(case)
+    psi_o, perf_o = O.World([s]).solve(ctl, s["psi0"].copy(), s["source"])
+    psi_r, perf_r = O.ref_solve(s, ctl)
+    assert perf_r["singular"] and not perf_r["converged"] and perf_r["nIterations"] == 0
+    for key in ("initialResidual", "finalResidual", "nIterations", "converged", "singular"):
+        assert perf_o[key] == perf_r[key], key
+    assert np.array_equal(psi_o[0], psi_r)
