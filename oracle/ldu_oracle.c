@@ -69,6 +69,9 @@ struct orc_world {
     orc_hierarchy* h;         /* [R] or NULL */
     int hBuilt;
     int diagonalOnly;         /* lduMatrix::diagonal(): no upper and no lower coefficients were ever set */
+    /* agglomeration kept from an earlier solve with cacheAgglomeration on (GAMGAgglomeration is a
+     * MeshObject: GAMGAgglomeration.C:97-140 looks it up before building one) */
+    int cached;
 };
 
 /* lduMatrix::H: LM/lduMatrix/lduMatrixTemplates.C:33-65 (off-diagonal product, negated;
@@ -1214,6 +1217,22 @@ int orc_gamg_build(orc_world* w, const orc_controls* ctl)
     double** fw = (double**)calloc((size_t)R, sizeof(double*));
     int* fwOwned = (int*)calloc((size_t)R, sizeof(int));
 
+    if (w->cached) {
+        /* the agglomeration found on the mesh is used whatever this dictionary says about
+         * agglomerator / mergeLevels / nCellsInCoarsestLevel; coefficients are agglomerated afresh */
+        free(fw); free(fwOwned);
+        nCreated = w->h[0].nLevels;
+        for (i = 0; i < nCreated; i++)
+            for (r = 0; r < R; r++) {
+                orc_hierarchy* h = &w->h[r];
+                const orc_matrix* fm = i ? h->level[i - 1] : &w->m[r];
+                free(h->level[i]->own_diag); free(h->level[i]->own_upper); free(h->level[i]->own_lower);
+                agglomerate_matrix(fm, h->level[i], h->restrictAddr[i], h->faceRestrictAddr[i]);
+            }
+        if (!ctl->cacheAgglomeration) w->cached = 0;   /* this solver deletes it when it is done */
+        w->hBuilt = 1;
+        return 0;
+    }
     for (r = 0; r < R; r++) hierarchy_clear(&w->h[r]);
     w->hBuilt = 0;
 
@@ -1370,6 +1389,7 @@ int orc_gamg_build(orc_world* w, const orc_controls* ctl)
             agglomerate_matrix(fm, h->level[i], h->restrictAddr[i], h->faceRestrictAddr[i]);
         }
     w->hBuilt = 1;
+    w->cached = ctl->cacheAgglomeration ? 1 : 0;
     return 0;
 }
 

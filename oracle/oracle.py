@@ -36,7 +36,7 @@ class Controls(C.Structure):
         ("nFinestSweeps", C.c_int), ("interpolateCorrection", C.c_int),
         ("scaleCorrection", C.c_int), ("nVcycles", C.c_int),
         ("precTolerance", C.c_double), ("precRelTol", C.c_double),
-        ("useFaceWeights", C.c_int),
+        ("useFaceWeights", C.c_int), ("cacheAgglomeration", C.c_int),
     ]
 
 
@@ -137,6 +137,7 @@ def make_controls(d: dict) -> Controls:
     c.scaleCorrection = -1 if sc is None else int(bool(sc))
     c.nVcycles = int(src.get("nVcycles", 2))
     c.useFaceWeights = int(src.get("agglomerator", "faceAreaPair") == "faceAreaPair")
+    c.cacheAgglomeration = int(bool(src.get("cacheAgglomeration", False)))
     return c
 
 
@@ -162,13 +163,17 @@ class World:
         self.w = L.orc_world_new(self.R)
         self.nCells = []
         self.nFaces = []
+        self._coeffs = []
         for r, reg in enumerate(regions):
             lo = np.ascontiguousarray(reg["lower"], dtype=np.int32)
             up = np.ascontiguousarray(reg["upper"], dtype=np.int32)
             diag = _f64(reg["diag"])
             uc = _f64(np.zeros(0) if reg["upperCoef"] is None else reg["upperCoef"])
             lc = None if reg.get("lowerCoef") is None else _f64(reg["lowerCoef"])
+            # own copies: set_coeffs() overwrites them in place
+            diag, uc, lc = diag.copy(), uc.copy(), None if lc is None else lc.copy()
             self._keep += [lo, up, diag, uc, lc]
+            self._coeffs.append((diag, uc, lc))
             self.nCells.append(diag.size)
             self.nFaces.append(lo.size)
             L.orc_world_set_region(self.w, r, diag.size, lo.size, lo.ctypes.data, up.ctypes.data,
@@ -189,6 +194,14 @@ class World:
                 self._keep += [fc, bou, intc]
                 L.orc_world_add_interface(self.w, r, int(it["nbrRegion"]), int(it["nbrInterface"]),
                                           fc.size, fc.ctypes.data, bou.ctypes.data, intc.ctypes.data)
+
+    def set_coeffs(self, r, diag, upperCoef, lowerCoef=None):
+        """new coefficients on the same addressing (the arrays the C side borrows are updated in place)"""
+        d, u, lo = self._coeffs[r]
+        d[:] = diag
+        u[:] = upperCoef
+        if lo is not None:
+            lo[:] = lowerCoef
 
     def __del__(self):
         try:
@@ -451,6 +464,25 @@ def ref_run_par(regions, op, *args, psi=None, source=None, ints=False, timeout=3
         res = [np.fromfile(os.path.join(td, f"o{r}.bin"), dtype=np.int32 if ints else np.float64)
                for r in range(n)]
     return res, outs[0]
+
+
+def second_coeffs(sysd):
+    """the coefficient change of the driver's solve2 op (exact multipliers): (diag, upper, lower)"""
+    f = np.arange(np.asarray(sysd["upperCoef"]).size)
+    c = np.arange(np.asarray(sysd["diag"]).size)
+    m = 1 + 0.25 * ((7 * f) % 5)
+    lower = None if sysd.get("lowerCoef") is None else sysd["lowerCoef"] * m
+    return sysd["diag"] * (1.5 + 0.25 * (c % 3)), sysd["upperCoef"] * m, lower
+
+
+def parse_perfs(stdout: str):
+    out = []
+    for line in stdout.splitlines():
+        if line.startswith("PERF "):
+            t = line.split()
+            out.append(dict(solverName=t[1], initialResidual=float(t[2]), finalResidual=float(t[3]),
+                            nIterations=int(t[4]), converged=bool(int(t[5])), singular=bool(int(t[6]))))
+    return out
 
 
 def parse_perf(stdout: str) -> dict:

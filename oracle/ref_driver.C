@@ -14,6 +14,11 @@
       precondition <name>                      -> out = M^-1 source
       smooth "<dict text>" <nSweeps>           -> out = psi after sweeps
       solve  "<dict text>"                     -> out = psi; PERF line on stdout
+      solve2 "<dict text>"                     -> two solves on the same mesh: as given, then with
+                                                  upper/lower[f] *= 1 + 0.25*((7 f) % 5) and
+                                                  diag[c] *= 1.5 + 0.25*(c % 3), both from the file's
+                                                  psi; out = second psi; two PERF lines
+                                                  (cacheAgglomeration: GAMGSolver.C:70,144-154)
       agglom "<dict text>"                     -> out = int32 stream
                                                   nLevels, then per level
                                                   nFine, nCoarse, restrict[nFine]
@@ -637,6 +642,32 @@ int main(int argc, char* argv[])
         if (op == "time_solve")
         {
             printf("TIME %.9g\n", t);
+        }
+        out = psi;
+    }
+    else if (op == "solve2")
+    {
+        dictionary d(dictFromText(argv[4]));
+        const scalarField psi0(psi);
+        for (int pass = 0; pass < 2; pass++)
+        {
+            if (pass)
+            {
+                // exact multipliers (quarters), the same in oracle/oracle.py::second_coeffs
+                forAll(A.upper(), f)
+                {
+                    const scalar m = 1 + 0.25*((7*f) % 5);
+                    A.upper()[f] *= m;
+                    if (asym) A.lower()[f] *= m;
+                }
+                forAll(A.diag(), c) A.diag()[c] *= 1.5 + 0.25*(c % 3);
+            }
+            psi = psi0;
+            solverPerformance sp = lduMatrix::solver::New
+            (
+                "p", A, bouCoeffs, intCoeffs, interfaces, d
+            )->solve(psi, source);
+            printPerf(sp);
         }
         out = psi;
     }

@@ -178,6 +178,23 @@ EDGE_SOLVES = [
 ]
 
 
+# two solves on one mesh, coefficients changed in between (oracle.second_coeffs): with
+# cacheAgglomeration on, the second GAMG solve reuses the agglomeration of the first (a MeshObject in
+# the reference, GAMGSolver.C:70,144-154) -- for algebraicPair that is a different hierarchy than a
+# fresh one (18/8 iterations without the cache, 18/13 with it on box12_var)
+CACHE_SOLVES = [
+    ("box12_var", dict(_GAMG, agglomerator="algebraicPair", tolerance=1e-8, relTol=0, cacheAgglomeration=True)),
+    ("box12_var", dict(_GAMG, agglomerator="algebraicPair", tolerance=1e-8, relTol=0, cacheAgglomeration=False)),
+    ("box12_var", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0, cacheAgglomeration=True)),
+    ("asym10", dict(_GAMG, smoother="DILU", agglomerator="algebraicPair", tolerance=1e-8, relTol=0,
+                    cacheAgglomeration=True)),
+    ("box12_var", dict(solver="PCG", tolerance=1e-9, relTol=0,
+                       preconditioner=dict(preconditioner="GAMG", smoother="GaussSeidel", agglomerator="algebraicPair",
+                                           nCellsInCoarsestLevel=10, mergeLevels=1, cacheAgglomeration=True,
+                                           tolerance=1e-5, relTol=0, nVcycles=2))),
+]
+
+
 # singular systems (SolverPerformance::checkSingularity, SolverPerformance.C:31-52): an all-zero matrix
 # makes wApA vanish in the first iteration -> singular, not converged, no iteration counted
 SINGULAR_SOLVES = [

@@ -109,6 +109,17 @@ def main():
                                      perf["nIterations"], perf["converged"], perf["singular"]], dtype=np.float64)
         print("cyclic solve", i, name, ctl["solver"], perf["nIterations"])
     np.savez_compressed(HERE / "cyclic.npz", **cyc)
+    # two solves on one mesh with the agglomeration cached (or not) in between
+    cache = {}
+    for i, (name, ctl) in enumerate(cases.CACHE_SOLVES):
+        s = cases.system(name)
+        psi, so = O.ref_run(s, "solve2", O.dict_text(cases.ref_controls(ctl)))
+        p1, p2 = O.parse_perfs(so)
+        cache[f"psi_{i}"] = psi
+        cache[f"perf_{i}"] = np.array([p1["nIterations"], p1["finalResidual"], p2["nIterations"],
+                                       p2["finalResidual"]], dtype=np.float64)
+        print("cached agglomeration", i, name, p1["nIterations"], p2["nIterations"])
+    np.savez_compressed(HERE / "cache_solves.npz", **cache)
     # edge cases of the solver front end
     edge = {}
     for i in range(len(cases.EDGE_SOLVES)):

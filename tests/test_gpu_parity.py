@@ -413,3 +413,27 @@ def test_singular_matrix(ctx, case):
     assert np.array_equal(psi, psi_o[0])
     assert str(perf).endswith("solution singularity")
     A.destroy()
+
+
+@pytest.mark.parametrize("case", range(len(cases.CACHE_SOLVES)))
+def test_cached_agglomeration_across_solves(ctx, case):
+    """cacheAgglomeration: the second solve on the mesh (new coefficients) reuses the agglomeration of
+    the first, as the reference's MeshObject does -- against the REFERENCE's committed results"""
+    import ldub200
+    g = np.load(cases.__file__.replace("cases.py", "golden/cache_solves.npz"))
+    name, ctl = cases.CACHE_SOLVES[case]
+    s = cases.system(name)
+    O = _oracle()
+    A = _matrix(ctx, s)
+    exact = dict(ctl, referenceOrderSums=True)
+    psi = s["psi0"].copy()
+    perf1 = ldub200.lduMatrix.solver.New("p", A, exact).solve(psi, s["source"])
+    d2, u2, l2 = O.second_coeffs(s)
+    A.set_coeffs(d2, u2, l2)
+    psi = s["psi0"].copy()
+    perf2 = ldub200.lduMatrix.solver.New("p", A, exact).solve(psi, s["source"])
+    ref = g[f"perf_{case}"]
+    assert (perf1.nIterations, perf1.finalResidual) == (int(ref[0]), ref[1])
+    assert (perf2.nIterations, perf2.finalResidual) == (int(ref[2]), ref[3])
+    assert np.array_equal(psi, g[f"psi_{case}"])
+    A.destroy()

@@ -179,3 +179,18 @@ def test_singular_matrix(case):
     assert perf["singular"] and not perf["converged"] and perf["nIterations"] == 0
     assert perf["initialResidual"] == 1.0 and perf["finalResidual"] == 1.0
     assert np.array_equal(psi[0], s["psi0"])
+
+
+@pytest.mark.parametrize("case", range(len(cases.CACHE_SOLVES)))
+def test_cached_agglomeration_across_solves(case):
+    g = np.load(GOLD / "cache_solves.npz")
+    name, ctl = cases.CACHE_SOLVES[case]
+    s = cases.system(name)
+    w = O.World([s])
+    _, perf1 = w.solve(ctl, s["psi0"].copy(), s["source"])
+    w.set_coeffs(0, *O.second_coeffs(s))
+    psi2, perf2 = w.solve(ctl, s["psi0"].copy(), s["source"])
+    ref = g[f"perf_{case}"]
+    assert (perf1["nIterations"], perf1["finalResidual"]) == (int(ref[0]), ref[1])
+    assert (perf2["nIterations"], perf2["finalResidual"]) == (int(ref[2]), ref[3])
+    assert np.array_equal(psi2[0], g[f"psi_{case}"])

@@ -160,3 +160,19 @@ def test_singular_matrix(case):
     for key in ("initialResidual", "finalResidual", "nIterations", "converged", "singular"):
         assert perf_o[key] == perf_r[key], key
     assert np.array_equal(psi_o[0], psi_r)
+
+
+@pytest.mark.parametrize("case", range(len(cases.CACHE_SOLVES)))
+def test_cached_agglomeration_across_solves(case):
+    """two solves on the same mesh with changed coefficients in between (driver op solve2)"""
+    name, ctl = cases.CACHE_SOLVES[case]
+    s = cases.system(name)
+    w = O.World([s])
+    _, perf1 = w.solve(ctl, s["psi0"].copy(), s["source"])
+    w.set_coeffs(0, *O.second_coeffs(s))
+    psi2, perf2 = w.solve(ctl, s["psi0"].copy(), s["source"])
+    psi_r, so = O.ref_run(s, "solve2", O.dict_text(cases.ref_controls(ctl)))
+    ref1, ref2 = O.parse_perfs(so)
+    assert perf1["nIterations"] == ref1["nIterations"] and perf1["finalResidual"] == ref1["finalResidual"]
+    assert perf2["nIterations"] == ref2["nIterations"] and perf2["finalResidual"] == ref2["finalResidual"]
+    assert np.array_equal(psi2[0], psi_r)
