@@ -133,6 +133,9 @@ def main():
         srcs = [HERE / "ref_driver.C"] + sorted((HERE / "pstream_shm").glob("*"))
         newest = max(p.stat().st_mtime for p in srcs)
         outs = [OUT / "ref_driver", OUT / "ref_driver_par", OUT / "libPstream_shm.so"]
+        if not (BUILD / "lnInclude" / "lduMatrix.H").exists():
+            # scratch directory gone (new container): the plug-in build needs the flat include directory
+            (OUT / "lnInclude.txt").write_text(str(prepare_lninclude()) + "\n")
         if all(o.exists() and o.stat().st_mtime >= newest for o in outs):
             return 0
         return build_driver(prepare_lninclude())
