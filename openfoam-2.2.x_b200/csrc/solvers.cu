@@ -474,6 +474,12 @@ static int krylov_solve(ldu_matrix* m, const ldu_controls* c, double* psi, const
     if (hs.done) return LDU_OK;
 
     const bool useGamg = (c->preconditioner == LDU_PRECOND_GAMG);
+    if (bicg && useGamg) {
+        // GAMGPreconditioner has no preconditionT: the reference stops in the first PBiCG iteration with
+        // "Not implemented" (lduMatrix.H:492-505 called from PBiCG.C:139)
+        set_error("PBiCG with preconditioner GAMG: GAMG::preconditionT is not implemented (as in the reference)");
+        return LDU_EINVAL;
+    }
     Precond pre;
     if (!useGamg) LDU_TRY(precond_setup(m, c->preconditioner, pre, W_RD));
     const bool cheap = (c->preconditioner == LDU_PRECOND_NONE || c->preconditioner == LDU_PRECOND_DIAGONAL);

@@ -1677,6 +1677,9 @@ int orc_solve(orc_world* w, const orc_controls* c, double** psi, double** source
         krylov_solve(w, w->m, w->R, c, psi, source, perf, residualHistory, histCap, 0);
         return 0;
     case ORC_SOLVER_PBICG:
+        /* GAMGPreconditioner has no preconditionT: the reference stops with "Not implemented"
+         * in the first iteration (lduMatrix.H:492-505, PBiCG.C:139) */
+        if (c->preconditioner == ORC_PRECOND_GAMG) return -1;
         krylov_solve(w, w->m, w->R, c, psi, source, perf, residualHistory, histCap, 1);
         return 0;
     case ORC_SOLVER_SMOOTH:

@@ -178,6 +178,34 @@ EDGE_SOLVES = [
 ]
 
 
+# GAMG controls beyond GAMG_SOLVES (GAMGSolver.C:157-181): sweep counts with level multipliers and caps,
+# explicit scaleCorrection on either matrix type, interpolateCorrection on an asymmetric matrix, the
+# remaining smoothers on the levels, GAMG preconditioner variants.  Pinned on the oracle against the
+# reference (CPU); the CUDA path reads the same controls and is checked on these in the next round.
+GAMG_OPTION_SOLVES = [
+    ("box12_var", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0, nPreSweeps=1,
+                       preSweepsLevelMultiplier=2, maxPreSweeps=3)),
+    ("box12_var", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0, nPostSweeps=1,
+                       postSweepsLevelMultiplier=3, maxPostSweeps=5, nFinestSweeps=3)),
+    ("box12_var", dict(_GAMG, agglomerator="algebraicPair", tolerance=1e-8, relTol=0, scaleCorrection=False)),
+    ("asym10", dict(_GAMG, agglomerator="faceAreaPair", tolerance=1e-8, relTol=0, scaleCorrection=True)),
+    ("asym10", dict(_GAMG, agglomerator="algebraicPair", tolerance=1e-8, relTol=0, interpolateCorrection=True,
+                    nPreSweeps=1)),
+    ("box9x7x5_dirichlet", dict(_GAMG, smoother="DICGaussSeidel", agglomerator="faceAreaPair", tolerance=1e-9,
+                                relTol=0, nFinestSweeps=1, nPostSweeps=3)),
+    ("asym10", dict(_GAMG, smoother="DILUGaussSeidel", agglomerator="faceAreaPair", tolerance=1e-8, relTol=0,
+                    mergeLevels=2)),
+    ("cavity20x20", dict(_GAMG, smoother="FDIC", agglomerator="algebraicPair", tolerance=1e-8, relTol=0,
+                         nCellsInCoarsestLevel=50)),
+    ("scrambled17", dict(_GAMG, smoother="symGaussSeidel", agglomerator="faceAreaPair", tolerance=1e-7, relTol=0,
+                         mergeLevels=2, nPreSweeps=2, maxPreSweeps=2)),
+    ("box12_var", dict(solver="PCG", tolerance=1e-9, relTol=0,
+                       preconditioner=dict(preconditioner="GAMG", smoother="DIC", agglomerator="algebraicPair",
+                                           nCellsInCoarsestLevel=10, mergeLevels=1, cacheAgglomeration=False,
+                                           tolerance=1e-5, relTol=0, nVcycles=1, nPreSweeps=1))),
+]
+
+
 # two solves on one mesh, coefficients changed in between (oracle.second_coeffs): with
 # cacheAgglomeration on, the second GAMG solve reuses the agglomeration of the first (a MeshObject in
 # the reference, GAMGSolver.C:70,144-154) -- for algebraicPair that is a different hierarchy than a

@@ -109,6 +109,16 @@ def main():
                                      perf["nIterations"], perf["converged"], perf["singular"]], dtype=np.float64)
         print("cyclic solve", i, name, ctl["solver"], perf["nIterations"])
     np.savez_compressed(HERE / "cyclic.npz", **cyc)
+    # GAMG controls beyond GAMG_SOLVES: digests of the reference's solutions
+    gopt = {}
+    for i, (name, ctl) in enumerate(cases.GAMG_OPTION_SOLVES):
+        s = cases.system(name)
+        psi, perf = O.ref_solve(s, cases.ref_controls(ctl))
+        gopt[f"sha_psi_{i}"] = cases.digest(psi)
+        gopt[f"perf_{i}"] = np.array([perf["initialResidual"], perf["finalResidual"], perf["nIterations"],
+                                      perf["converged"]], dtype=np.float64)
+        print("GAMG option", i, name, perf["nIterations"])
+    np.savez_compressed(HERE / "gamg_options.npz", **gopt)
     # two solves on one mesh with the agglomeration cached (or not) in between
     cache = {}
     for i, (name, ctl) in enumerate(cases.CACHE_SOLVES):

@@ -194,3 +194,15 @@ def test_cached_agglomeration_across_solves(case):
     assert (perf1["nIterations"], perf1["finalResidual"]) == (int(ref[0]), ref[1])
     assert (perf2["nIterations"], perf2["finalResidual"]) == (int(ref[2]), ref[3])
     assert np.array_equal(psi2[0], g[f"psi_{case}"])
+
+
+@pytest.mark.parametrize("case", range(len(cases.GAMG_OPTION_SOLVES)))
+def test_gamg_options(case):
+    g = np.load(GOLD / "gamg_options.npz")
+    name, ctl = cases.GAMG_OPTION_SOLVES[case]
+    s = cases.system(name)
+    psi, perf = O.World([s]).solve(ctl, s["psi0"].copy(), s["source"])
+    ref = g[f"perf_{case}"]
+    assert perf["initialResidual"] == ref[0] and perf["finalResidual"] == ref[1]
+    assert perf["nIterations"] == int(ref[2]) and perf["converged"] == bool(ref[3])
+    assert np.array_equal(cases.digest(psi[0]), g[f"sha_psi_{case}"])

@@ -176,3 +176,28 @@ def test_cached_agglomeration_across_solves(case):
     assert perf1["nIterations"] == ref1["nIterations"] and perf1["finalResidual"] == ref1["finalResidual"]
     assert perf2["nIterations"] == ref2["nIterations"] and perf2["finalResidual"] == ref2["finalResidual"]
     assert np.array_equal(psi2[0], psi_r)
+
+
+def test_pbicg_with_gamg_preconditioner_is_an_error():
+    """GAMGPreconditioner implements precondition() only; PBiCG needs preconditionT() and the reference
+    stops with "Not implemented" (lduMatrix.H:492-505).  Oracle and library refuse the combination."""
+    s = cases.system("asym10")
+    ctl = dict(solver="PBiCG", tolerance=1e-9, relTol=0,
+               preconditioner=dict(preconditioner="GAMG", smoother="GaussSeidel", agglomerator="algebraicPair",
+                                   nCellsInCoarsestLevel=10, mergeLevels=1, cacheAgglomeration=False,
+                                   tolerance=1e-5, relTol=0, nVcycles=2))
+    with pytest.raises(AssertionError):
+        O.World([s]).solve(ctl, s["psi0"].copy(), s["source"])
+    with pytest.raises(RuntimeError, match="Not implemented"):
+        O.ref_solve(s, ctl)
+
+
+@pytest.mark.parametrize("case", range(len(cases.GAMG_OPTION_SOLVES)))
+def test_gamg_options(case):
+    name, ctl = cases.GAMG_OPTION_SOLVES[case]
+    s = cases.system(name)
+    psi_o, perf_o = O.World([s]).solve(ctl, s["psi0"].copy(), s["source"])
+    psi_r, perf_r = O.ref_solve(s, cases.ref_controls(ctl))
+    for key in ("initialResidual", "finalResidual", "nIterations", "converged"):
+        assert perf_o[key] == perf_r[key], key
+    assert np.array_equal(psi_o[0], psi_r)
