@@ -373,6 +373,13 @@ int smootherKind(const word& name)
 // GAMG keys (GAMGSolver.C:157-181, GAMGAgglomeration.C:77-80, pairGAMGAgglomeration.C:45)
 void readGamgControls(const dictionary& d, ldu_controls& c)
 {
+    // the dense LU solve of the coarsest level (GAMGSolver.C:74,91-106) is outside this library:
+    // say so instead of silently running the iterative coarsest-level solver
+    if (d.lookupOrDefault<Switch>("directSolveCoarsest", false))
+    {
+        FatalErrorIn("gpuLduSolver") << "directSolveCoarsest is not supported by the GPU GAMG solver"
+            << exit(FatalError);
+    }
     c.nCellsInCoarsestLevel = d.lookupOrDefault<label>("nCellsInCoarsestLevel", 10);
     c.mergeLevels = d.lookupOrDefault<label>("mergeLevels", 1);
     c.nPreSweeps = d.lookupOrDefault<label>("nPreSweeps", 0);

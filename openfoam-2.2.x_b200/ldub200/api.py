@@ -147,6 +147,10 @@ def make_controls(d: dict) -> Controls:
     if name not in SOLVERS:
         # lduMatrixSolver.C:96-110: unknown solver is a FatalIOError listing the table
         raise LduError(f"Unknown solver {name}; valid solvers are {sorted(SOLVERS)}")
+    if d.get("directSolveCoarsest") or (isinstance(d.get("preconditioner"), dict)
+                                        and d["preconditioner"].get("directSolveCoarsest")):
+        # the dense LU solve of the coarsest level (GAMGSolver.C:74,91-106) is outside this library
+        raise LduError("directSolveCoarsest is not supported")
     c.solver = SOLVERS[name]
     pre = d.get("preconditioner", "none")
     sub = d

@@ -97,3 +97,9 @@ def test_iccg_biccg_aliases_and_mandatory_preconditioner():
     for name in ("PCG", "PBiCG", "ICCG", "BICCG"):
         with pytest.raises(ldub200.LduError, match="preconditioner"):
             ldub200.make_controls(dict(solver=name, tolerance=1e-8))
+
+
+def test_direct_solve_coarsest_is_refused():
+    with pytest.raises(ldub200.LduError, match="directSolveCoarsest"):
+        ldub200.make_controls(dict(solver="GAMG", smoother="GaussSeidel", directSolveCoarsest=True))
+    ldub200.make_controls(dict(solver="GAMG", smoother="GaussSeidel", directSolveCoarsest=False))
