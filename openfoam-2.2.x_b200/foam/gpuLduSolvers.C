@@ -380,8 +380,10 @@ void readGamgControls(const dictionary& d, ldu_controls& c)
         FatalErrorIn("gpuLduSolver") << "directSolveCoarsest is not supported by the GPU GAMG solver"
             << exit(FatalError);
     }
-    c.nCellsInCoarsestLevel = d.lookupOrDefault<label>("nCellsInCoarsestLevel", 10);
-    c.mergeLevels = d.lookupOrDefault<label>("mergeLevels", 1);
+    // mandatory in the reference: GAMGAgglomeration.C:77-80 reads it without a default
+    c.nCellsInCoarsestLevel = readLabel(d.lookup("nCellsInCoarsestLevel"));
+    // mandatory in the reference: pairGAMGAgglomeration.C:45 reads it without a default
+    c.mergeLevels = readLabel(d.lookup("mergeLevels"));
     c.nPreSweeps = d.lookupOrDefault<label>("nPreSweeps", 0);
     c.preSweepsLevelMultiplier = d.lookupOrDefault<label>("preSweepsLevelMultiplier", 1);
     c.maxPreSweeps = d.lookupOrDefault<label>("maxPreSweeps", 4);
@@ -396,13 +398,21 @@ void readGamgControls(const dictionary& d, ldu_controls& c)
     }
     c.cacheAgglomeration = d.lookupOrDefault<Switch>("cacheAgglomeration", false);
     c.nVcycles = d.lookupOrDefault<label>("nVcycles", 2);
-    if (d.found("smoother"))
-    {
-        c.smoother = smootherKind(word(d.lookup("smoother")));
-    }
-    // faceAreaPair needs fvMesh::Sf() (libfiniteVolume); until the weights are
-    // handed over the algebraic pair agglomerator is used for every name
+    // mandatory in the reference (lduMatrixSmoother.C:38-66, GAMGAgglomeration.C:104-107)
+    c.smoother = smootherKind(word(d.lookup("smoother")));
+    const word agglomerator(d.lookup("agglomerator"));
+    // faceAreaPair needs fvMesh::Sf() (libfiniteVolume), which this shim cannot reach: every pair
+    // agglomerator runs as algebraicPair here.  Said once, because the iteration counts then differ
+    // from the reference's faceAreaPair (the C ABI and the Python host do take face weights).
     c.useFaceWeights = 0;
+    static bool warned = false;
+    if (agglomerator != "algebraicPair" && !warned)
+    {
+        warned = true;
+        WarningIn("gpuLduSolver")
+            << "agglomerator " << agglomerator << " runs as algebraicPair in the GPU plug-in"
+            << " (face areas are not available to it)" << endl;
+    }
 }
 
 } // End anonymous namespace
@@ -445,8 +455,9 @@ void Foam::gpuLduSolver::fillControls(ldu_controls& c) const
     c.referenceOrderSums =
         controlDict_.lookupOrDefault<Switch>("referenceOrderSums", false);
 
-    if (controlDict_.found("smoother"))
+    if (solverKind() == LDU_SOLVER_SMOOTH)
     {
+        // mandatory in the reference (lduMatrixSmoother.C:38-66)
         c.smoother = smootherKind(word(controlDict_.lookup("smoother")));
     }
 
@@ -456,7 +467,7 @@ void Foam::gpuLduSolver::fillControls(ldu_controls& c) const
         c.preconditioner =
             preconditionerKind(lduMatrix::preconditioner::getName(controlDict_));
         const entry& e = controlDict_.lookupEntry("preconditioner", false, false);
-        if (e.isDict())
+        if (e.isDict() && c.preconditioner == LDU_PRECOND_GAMG)
         {
             const dictionary& pd = e.dict();
             readGamgControls(pd, c);
@@ -478,6 +489,10 @@ Foam::solverPerformance Foam::gpuLduSolver::solve
     const direction
 ) const
 {
+    // dictionary errors first, as the reference's constructors raise them (readControls)
+    ldu_controls c;
+    fillControls(c);
+
     coupledPatches cp;
     findCoupledPatches(matrix_, interfaces_, cp);
     ldu_matrix* m = deviceMatrix(matrix_, cp);
@@ -503,9 +518,6 @@ Foam::solverPerformance Foam::gpuLduSolver::solve
         ),
         "ldu_matrix_set_coeffs"
     );
-
-    ldu_controls c;
-    fillControls(c);
 
     ldu_solver_performance p;
     check(ldu_solve(m, &c, psi.begin(), source.begin(), &p), "ldu_solve");
