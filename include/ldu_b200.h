@@ -183,6 +183,12 @@ int ldu_matrix_set_face_weights(ldu_matrix* m, const double* weights);
 int ldu_colour_order(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr,
                      int* newIndexOfOldCell, int* nColours);
 
+/* Cuthill-McKee band compression, host only: the numbering renumberMesh's default method gives
+ * (meshes/bandCompression/bandCompression.C:42-148 on the cell-cell addressing of the internal faces,
+ * restated with its quirks so that the result is the reference's).  oldCellOfNewCell[nCells] out. */
+int ldu_band_compression(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr,
+                         int* oldCellOfNewCell);
+
 /* ---- operators: host in / host out ---------------------------------------- */
 /* lduMatrix::Amul  matrices/lduMatrix/lduMatrix/lduMatrixATmul.C:34-92 */
 int ldu_amul(ldu_matrix* m, double* Apsi, const double* psi);

@@ -605,6 +605,65 @@ int ldu_colour_order(int nCells, int nFaces, const int* lowerAddr, const int* up
     return LDU_OK;
 }
 
+// Cuthill-McKee band compression as renumberMesh's default method applies it
+// (renumber/renumberMethods/CuthillMcKeeRenumber -> meshes/bandCompression/bandCompression.C:42-148):
+// breadth-first walk per connected component, each started from the lowest-numbered unvisited cell of
+// minimal degree; a visited cell appends its unvisited neighbours to the queue.  The reference
+// computes the degree-sorted order of those neighbours and then appends nbrs[i], not nbrs[order[i]]
+// (bandCompression.C:133-139) -- the neighbours go in cell-cell order (ascending face index); restated
+// as is, so that the numbering equals what renumberMesh produces.  Host only.
+// oldCellOfNewCell[new] = old (the reference's "newOrder").
+int ldu_band_compression(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr,
+                         int* oldCellOfNewCell)
+{
+    if (nCells < 0 || nFaces < 0 || !oldCellOfNewCell || (nFaces && (!lowerAddr || !upperAddr))) {
+        set_error("ldu_band_compression: bad argument");
+        return LDU_EINVAL;
+    }
+    // cell-cell addressing in face order (decompositionMethod::calcCellCells on the internal faces)
+    std::vector<int> start(nCells + 1, 0);
+    for (int f = 0; f < nFaces; f++) {
+        const int l = lowerAddr[f], u = upperAddr[f];
+        if (l < 0 || u < 0 || l >= nCells || u >= nCells || l == u) {
+            set_error("ldu_band_compression: addressing out of range");
+            return LDU_EINVAL;
+        }
+        start[l + 1]++;
+        start[u + 1]++;
+    }
+    for (int c = 0; c < nCells; c++) start[c + 1] += start[c];
+    std::vector<int> adj(start[nCells]), fill(start.begin(), start.end() - 1);
+    for (int f = 0; f < nFaces; f++) {
+        adj[fill[lowerAddr[f]]++] = upperAddr[f];
+        adj[fill[upperAddr[f]]++] = lowerAddr[f];
+    }
+    std::vector<char> visited(nCells, 0);
+    std::vector<int> queue;
+    queue.reserve((size_t)nCells + adj.size());
+    int placed = 0;
+    for (;;) {
+        int current = -1, minDegree = 0x7fffffff;
+        for (int c = 0; c < nCells; c++) {
+            if (!visited[c] && start[c + 1] - start[c] < minDegree) {
+                minDegree = start[c + 1] - start[c];
+                current = c;
+            }
+        }
+        if (current < 0) break;
+        queue.clear();
+        queue.push_back(current);
+        for (size_t head = 0; head < queue.size(); head++) {
+            const int c = queue[head];
+            if (visited[c]) continue;
+            visited[c] = 1;
+            oldCellOfNewCell[placed++] = c;
+            for (int k = start[c]; k < start[c + 1]; k++)
+                if (!visited[adj[k]]) queue.push_back(adj[k]);
+        }
+    }
+    return LDU_OK;
+}
+
 int ldu_matrix_set_face_weights(ldu_matrix* m, const double* weights)
 {
     if (!m || (m->nFaces && !weights)) return LDU_EINVAL;

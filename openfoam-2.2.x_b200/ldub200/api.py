@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "ldu_context_synchronize", "ldu_context_stream", "ldu_comm_window_create", "ldu_comm_connect",
     "ldu_device_alloc", "ldu_device_free", "ldu_copy_h2d", "ldu_copy_d2h", "ldu_device_memset", "ldu_host_alloc",
     "ldu_host_free", "ldu_matrix_create", "ldu_matrix_destroy", "ldu_matrix_set_coeffs",
-    "ldu_matrix_set_coeffs_device", "ldu_matrix_set_face_weights", "ldu_colour_order", "ldu_amul", "ldu_tmul", "ldu_sumA", "ldu_H", "ldu_H1", "ldu_faceH", "ldu_H_device",
+    "ldu_matrix_set_coeffs_device", "ldu_matrix_set_face_weights", "ldu_colour_order", "ldu_band_compression", "ldu_amul", "ldu_tmul", "ldu_sumA", "ldu_H", "ldu_H1", "ldu_faceH", "ldu_H_device",
     "ldu_residual", "ldu_precondition", "ldu_smooth", "ldu_solve", "ldu_amul_device", "ldu_tmul_device",
     "ldu_solve_device", "ldu_residual_history", "ldu_gamg_build", "ldu_gamg_nlevels",
     "ldu_gamg_level_sizes", "ldu_gamg_level_restrict", "ldu_gamg_level_coeffs", "ldu_controls_default",

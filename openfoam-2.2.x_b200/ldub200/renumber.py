@@ -78,3 +78,24 @@ def sweep_depth(nCells: int, lower, upper) -> int:
         if d > depth[u]:
             depth[u] = d
     return int(depth.max()) + 1 if nCells else 0
+
+
+def band_compression(nCells: int, lower, upper):
+    """Cuthill-McKee numbering of renumberMesh's default method (ldu_band_compression, host):
+    returns perm with perm[old cell] = new cell, ready for `permute`."""
+    L = api.library()
+    lo = np.ascontiguousarray(lower, dtype=np.int32)
+    up = np.ascontiguousarray(upper, dtype=np.int32)
+    new_to_old = np.empty(nCells, dtype=np.int32)
+    rc = L.ldu_band_compression(nCells, lo.size, lo.ctypes.data, up.ctypes.data, new_to_old.ctypes.data)
+    if rc != 0:
+        raise api.LduError(f"ldu_band_compression failed ({rc}): {L.ldu_last_error().decode()}")
+    perm = np.empty(nCells, dtype=np.int64)
+    perm[new_to_old] = np.arange(nCells)
+    return perm
+
+
+def bandwidth(lower, upper) -> int:
+    """largest |upper - lower| over the faces (the profile the gathers of Amul walk)"""
+    lower, upper = np.asarray(lower, dtype=np.int64), np.asarray(upper, dtype=np.int64)
+    return int(np.abs(upper - lower).max()) if lower.size else 0

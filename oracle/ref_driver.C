@@ -22,6 +22,8 @@
       agglom "<dict text>"                     -> out = int32 stream
                                                   nLevels, then per level
                                                   nFine, nCoarse, restrict[nFine]
+      bandCompression                          -> out = int32 newOrder[nCells] of Foam::bandCompression on
+                                                  the cell-cell addressing of the internal faces
       time_amul <reps>                         -> TIME line (seconds per Amul)
       time_solve "<dict text>"                 -> TIME + PERF lines
   Environment: LDU_REF_LIBS=<lib.so> is opened through the Time's dlLibraryTable before the
@@ -73,6 +75,7 @@
 #include "IPstream.H"
 #include "OPstream.H"
 #include "dlLibraryTable.H"
+#include "bandCompression.H"
 
 #include <cstdio>
 #include <cstdlib>
@@ -709,6 +712,22 @@ int main(int argc, char* argv[])
             A.Amul(out, psi, bouCoeffs, interfaces, 0);
         }
         printf("TIME %.9g\n", timer.elapsedTime()/reps);
+    }
+    else if (op == "bandCompression")
+    {
+        // cell-cell addressing as decompositionMethod::calcCellCells builds it: face order
+        labelList nNbrs(nCells, 0);
+        forAll(l, f) { nNbrs[l[f]]++; nNbrs[u[f]]++; }
+        labelListList cellCells(nCells);
+        forAll(cellCells, c) { cellCells[c].setSize(nNbrs[c]); nNbrs[c] = 0; }
+        forAll(l, f)
+        {
+            cellCells[l[f]][nNbrs[l[f]]++] = u[f];
+            cellCells[u[f]][nNbrs[u[f]]++] = l[f];
+        }
+        const labelList order(bandCompression(cellCells));
+        intsOut = true;
+        forAll(order, i) outInts.push_back(order[i]);
     }
     else if (op == "agglom")
     {
