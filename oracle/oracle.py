@@ -1,5 +1,7 @@
 """ctypes front end of oracle/libldu_oracle.so (the CPU restatement) and of the
-compiled reference driver oracle/_ref/ref_driver.
+compiled reference drivers: oracle/_ref/ref_driver (one process) and
+oracle/_ref/ref_driver_par (one process per mesh region, coupled through the
+shared-memory Pstream of oracle/pstream_shm).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  Never by the product.
