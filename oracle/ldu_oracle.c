@@ -72,6 +72,7 @@ struct orc_world {
     /* agglomeration kept from an earlier solve with cacheAgglomeration on (GAMGAgglomeration is a
      * MeshObject: GAMGAgglomeration.C:97-140 looks it up before building one) */
     int cached;
+    int failed;               /* a solve stopped where the reference raises a FatalError */
 };
 
 /* lduMatrix::H: LM/lduMatrix/lduMatrixTemplates.C:33-65 (off-diagonal product, negated;
@@ -845,7 +846,9 @@ static void krylov_solve(orc_world* w, orc_matrix* ms, int R, const orc_controls
         orc_precond pre;
         int useGamg = (ctl->preconditioner == ORC_PRECOND_GAMG);
         if (!useGamg) precond_init(&pre, ms, R, ctl->preconditioner);
-        do {
+        /* GAMGPreconditioner is constructed here (PCG.C:111-115): no coarse level -> FatalError */
+        if (useGamg && !w->hBuilt && orc_gamg_build(w, ctl)) w->failed = 1;
+        else do {
             double wApA, alpha;
             wArAold = wArA;
             if (useGamg) {
@@ -1674,8 +1677,9 @@ int orc_solve(orc_world* w, const orc_controls* c, double** psi, double** source
     }
     switch (c->solver) {
     case ORC_SOLVER_PCG:
+        w->failed = 0;
         krylov_solve(w, w->m, w->R, c, psi, source, perf, residualHistory, histCap, 0);
-        return 0;
+        return w->failed ? -1 : 0;
     case ORC_SOLVER_PBICG:
         /* GAMGPreconditioner has no preconditionT: the reference stops with "Not implemented"
          * in the first iteration (lduMatrix.H:492-505, PBiCG.C:139) */

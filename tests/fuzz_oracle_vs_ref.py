@@ -1,0 +1,125 @@
+"""Differential fuzzing of the CPU restatement against the compiled reference (not collected by
+pytest; `python tests/fuzz_oracle_vs_ref.py [nCases] [seed]`).  Random LDU graphs (not meshes: any
+upper-triangular addressing), symmetric or asymmetric coefficients, random solver dictionaries,
+initial guesses and partitions into 1-3 regions; everything must agree bit for bit.
+tests/test_fuzz_seeded.py runs a short fixed-seed slice of the same generator."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / "openfoam-2.2.x_b200"), str(ROOT / "tests")]
+
+import cases  # noqa: E402
+from ldub200 import decompose  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def random_system(rng):
+    n = int(rng.integers(1, 70))
+    # a spanning chain (so GAMG can agglomerate) plus random extra faces
+    pairs = set()
+    order = rng.permutation(n)
+    for a, b in zip(order[:-1], order[1:]):
+        if rng.random() < 0.9:
+            pairs.add((min(a, b), max(a, b)))
+    for _ in range(int(rng.integers(0, 3 * n + 1))):
+        a, b = rng.integers(0, n, 2)
+        if a != b:
+            pairs.add((min(a, b), max(a, b)))
+    faces = sorted(pairs)
+    lower = np.array([p[0] for p in faces], dtype=np.int32)
+    upper = np.array([p[1] for p in faces], dtype=np.int32)
+    nf = lower.size
+    asym = bool(rng.random() < 0.4)
+    up = rng.uniform(0.2, 1.5, nf)
+    lo = up * rng.uniform(0.6, 1.4, nf) if asym else None
+    diag = np.zeros(n)
+    np.subtract.at(diag, lower, up if lo is None else lo)
+    np.subtract.at(diag, upper, up)
+    diag -= rng.uniform(0.05, 0.5, n)            # strictly dominant
+    return dict(nCells=n, nFaces=nf, lower=lower, upper=upper, diag=diag, upperCoef=up, lowerCoef=lo,
+                source=rng.standard_normal(n), psi0=np.zeros(n), faceWeights=rng.uniform(0.5, 2.0, nf))
+
+
+def random_controls(rng, s, multi):
+    asym = s["lowerCoef"] is not None
+    smoothers = [x for x in cases.SMOOTHERS if cases.selectable(s, x)]
+    kind = rng.choice(["krylov", "smooth", "gamg", "krylov_gamg"], p=[0.4, 0.2, 0.3, 0.1])
+    tol = float(rng.choice([1e-4, 1e-7, 1e-10]))
+    common = dict(tolerance=tol, relTol=float(rng.choice([0, 0, 0.01])), maxIter=int(rng.choice([3, 40, 1000])))
+    gamg = dict(smoother=str(rng.choice(smoothers)), agglomerator=str(rng.choice(["algebraicPair", "faceAreaPair"])),
+                nCellsInCoarsestLevel=int(rng.choice([2, 4, 10])), mergeLevels=int(rng.choice([1, 1, 2, 3])),
+                cacheAgglomeration=False, nPreSweeps=int(rng.choice([0, 0, 1, 2])),
+                nPostSweeps=int(rng.choice([1, 2, 3])), nFinestSweeps=int(rng.choice([1, 2])),
+                interpolateCorrection=bool(rng.random() < 0.2))
+    if rng.random() < 0.3:
+        gamg["scaleCorrection"] = bool(rng.random() < 0.5)
+    if kind == "krylov":
+        pres = [p for p in cases.PRECONDITIONERS if cases.selectable(s, p)]
+        return dict(common, solver="PBiCG" if asym else "PCG", preconditioner=str(rng.choice(pres)))
+    if kind == "smooth":
+        return dict(common, solver="smoothSolver", smoother=str(rng.choice(smoothers)),
+                    nSweeps=int(rng.choice([1, 2, 3])))
+    if kind == "gamg" or asym:
+        return dict(common, solver="GAMG", **gamg)
+    return dict(common, solver="PCG", preconditioner=dict(gamg, preconditioner="GAMG", tolerance=1e-4, relTol=0,
+                                                          nVcycles=int(rng.choice([1, 2]))))
+
+
+def one_case(seed):
+    """-> None if oracle and reference agree (or both refuse), else a description of the difference"""
+    rng = np.random.default_rng(seed)
+    s = random_system(rng)
+    R = int(rng.choice([1, 1, 2, 3])) if s["nCells"] >= 6 and O.ref_par_available() else 1
+    ctl = random_controls(rng, s, R > 1)
+    psi0 = rng.standard_normal(s["nCells"]) if rng.random() < 0.5 else np.zeros(s["nCells"])
+    if R == 1:
+        regs = [s]
+    else:
+        proc = rng.integers(0, R, s["nCells"]).astype(np.int32)
+        proc[:R] = np.arange(R)                       # no empty region
+        regs = decompose.decompose(s, proc, R)
+    psis = [psi0[r["cells"]] for r in regs] if R > 1 else [psi0]
+    srcs = [r["source"] for r in regs]
+    try:
+        po, perf = O.World(regs).solve(ctl, [p.copy() for p in psis], srcs)
+        mine = (perf, po)
+    except AssertionError:
+        mine = None
+    try:
+        if R == 1:
+            pr, so = O.ref_run(s, "solve", O.dict_text(cases.ref_controls(ctl)), psi=psi0)
+            pr = [pr]
+        else:
+            pr, so = O.ref_run_par(regs, "solve", O.dict_text(cases.ref_controls(ctl)), psi=psis, timeout=120)
+        ref = (O.parse_perf(so), pr)
+    except RuntimeError as e:
+        ref = None
+        err = str(e)
+    if mine is None and ref is None:
+        return None
+    if mine is None or ref is None:
+        return f"seed {seed}: one side refused (oracle ok={mine is not None}, reference ok={ref is not None}) " \
+               f"n={s['nCells']} R={R} ctl={ctl}" + ("" if ref else " :: " + err[-300:])
+    for key in ("initialResidual", "finalResidual", "nIterations", "converged", "singular"):
+        a, b = mine[0][key], ref[0][key]
+        if not (a == b or (a != a and b != b)):
+            return f"seed {seed}: {key} {a} != {b}  n={s['nCells']} nf={s['nFaces']} R={R} ctl={ctl}"
+    for a, b in zip(mine[1], ref[1]):
+        if not np.array_equal(a, b, equal_nan=True):
+            return f"seed {seed}: psi differs (max {np.abs(a - b).max():.3e}) n={s['nCells']} R={R} ctl={ctl}"
+    return None
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    bad = 0
+    for k in range(n):
+        msg = one_case(seed0 + k)
+        if msg:
+            bad += 1
+            print(msg, flush=True)
+    print(f"{n} cases from seed {seed0}: {bad} differences")
