@@ -68,6 +68,68 @@ def random_controls(rng, s, multi):
                                                           nVcycles=int(rng.choice([1, 2]))))
 
 
+def add_random_cyclic(rng, reg, region):
+    """two disjoint random cell sets of the region coupled as a cyclic pair"""
+    n = reg["nCells"]
+    k = int(rng.integers(1, max(2, n // 3)))
+    cells = rng.permutation(n)
+    a, b = np.sort(cells[:k]), np.sort(cells[k:2 * k])
+    if b.size < k:
+        return
+    asym = reg["lowerCoef"] is not None
+    ku = rng.uniform(0.05, 0.3, k)
+    kl = ku * rng.uniform(0.7, 1.3, k) if asym else ku
+    reg["diag"] = reg["diag"].copy()
+    np.subtract.at(reg["diag"], a, ku)
+    np.subtract.at(reg["diag"], b, ku)
+    first = len(reg.setdefault("interfaces", []))
+    reg["interfaces"].append(dict(nbrRegion=region, nbrInterface=first + 1, faceCells=a.astype(np.int32),
+                                  bouCoeffs=-ku, intCoeffs=-kl))
+    reg["interfaces"].append(dict(nbrRegion=region, nbrInterface=first, faceCells=b.astype(np.int32),
+                                  bouCoeffs=-kl, intCoeffs=-ku))
+
+
+def one_operator_case(seed):
+    """operators, preconditioners, smoothers, agglomeration maps and band compression on a random system
+    (with a random cyclic pair every other time); -> None or a description of the difference"""
+    rng = np.random.default_rng(10_000_000 + seed)
+    s = random_system(rng)
+    if s["nCells"] >= 6 and rng.random() < 0.5:
+        add_random_cyclic(rng, s, 0)
+    w = O.World([s])
+    x = rng.standard_normal(s["nCells"])
+    src = s["source"]
+    for op, mine in (("amul", lambda: w.amul(x)[0]), ("tmul", lambda: w.tmul(x)[0]), ("suma", lambda: w.sumA()[0]),
+                     ("residual", lambda: w.residual(x, src)[0])):
+        if not np.array_equal(mine(), O.ref_run(s, op, psi=x)[0]):
+            return f"operator seed {seed}: {op} differs"
+    if not s.get("interfaces"):
+        for op, mine in (("H", lambda: w.H(x)[0]), ("H1", lambda: w.H1()[0])):
+            if not np.array_equal(mine(), O.ref_run(s, op, psi=x)[0]):
+                return f"operator seed {seed}: {op} differs"
+        if s["nFaces"] and not np.array_equal(w.faceH(x)[0], O.ref_run(s, "faceH", psi=x)[0]):
+            return f"operator seed {seed}: faceH differs"
+    for pre in cases.PRECONDITIONERS:
+        if cases.selectable(s, pre):
+            if not np.array_equal(w.precondition(pre, src)[0], O.ref_run(s, "precondition", pre)[0]):
+                return f"operator seed {seed}: preconditioner {pre} differs"
+    if s["lowerCoef"] is not None:
+        if not np.array_equal(w.precondition("DILU", src, True)[0], O.ref_run(s, "preconditionT", "DILU")[0]):
+            return f"operator seed {seed}: DILU preconditionT differs"
+    nsw = int(rng.integers(1, 4))
+    for sm in cases.SMOOTHERS:
+        if cases.selectable(s, sm):
+            want = O.ref_run(s, "smooth", O.dict_text(dict(smoother=sm)), nsw, psi=x)[0]
+            if not np.array_equal(w.smooth(sm, x, src, nsw)[0], want):
+                return f"operator seed {seed}: smoother {sm} x{nsw} differs"
+    if not s.get("interfaces"):
+        from ldub200 import renumber
+        perm = renumber.band_compression(s["nCells"], s["lower"], s["upper"])
+        if not np.array_equal(np.argsort(perm), O.ref_run(s, "bandCompression", ints=True)[0]):
+            return f"operator seed {seed}: bandCompression differs"
+    return None
+
+
 def one_case(seed):
     """-> None if oracle and reference agree (or both refuse), else a description of the difference"""
     rng = np.random.default_rng(seed)
@@ -77,10 +139,15 @@ def one_case(seed):
     psi0 = rng.standard_normal(s["nCells"]) if rng.random() < 0.5 else np.zeros(s["nCells"])
     if R == 1:
         regs = [s]
+        if s["nCells"] >= 6 and rng.random() < 0.25:
+            add_random_cyclic(rng, s, 0)
     else:
         proc = rng.integers(0, R, s["nCells"]).astype(np.int32)
         proc[:R] = np.arange(R)                       # no empty region
         regs = decompose.decompose(s, proc, R)
+        for r, reg in enumerate(regs):
+            if reg["nCells"] >= 6 and rng.random() < 0.25:
+                add_random_cyclic(rng, reg, r)
     psis = [psi0[r["cells"]] for r in regs] if R > 1 else [psi0]
     srcs = [r["source"] for r in regs]
     try:
@@ -118,8 +185,8 @@ if __name__ == "__main__":
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     bad = 0
     for k in range(n):
-        msg = one_case(seed0 + k)
-        if msg:
-            bad += 1
-            print(msg, flush=True)
+        for msg in (one_case(seed0 + k), one_operator_case(seed0 + k) if k % 4 == 0 else None):
+            if msg:
+                bad += 1
+                print(msg, flush=True)
     print(f"{n} cases from seed {seed0}: {bad} differences")

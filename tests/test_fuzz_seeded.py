@@ -1,7 +1,8 @@
 """A fixed-seed slice of the differential fuzzer (tests/fuzz_oracle_vs_ref.py): random LDU graphs,
-coefficients, solver dictionaries, initial guesses and partitions into 1-3 regions; the CPU
-restatement and the compiled reference must agree bit for bit (or refuse the same inputs).
-The full campaigns run offline (1800 cases, 0 differences after the fixes they led to)."""
+coefficients, solver dictionaries, initial guesses, partitions into 1-3 regions and random cyclic
+pairs; the CPU restatement and the compiled reference must agree bit for bit (or refuse the same
+inputs).  The full campaigns run offline (2200 solve cases + 100 operator cases, 0 differences
+after the fix the first campaign led to)."""
 import pytest
 
 from oracle import oracle as O
@@ -15,3 +16,12 @@ def test_random_systems_agree_with_the_reference(block):
     # seeds 47, 58, 60, 61, 90, 107, 123 found the GAMG-preconditioner-without-coarse-levels case
     for seed in range(40 * block, 40 * block + 40):
         assert F.one_case(seed) is None
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_operators_smoothers_and_numberings_agree_with_the_reference(block):
+    """Amul family, H/H1/faceH, every preconditioner and smoother, band compression; a random cyclic
+    pair on every other system"""
+    import fuzz_oracle_vs_ref as F
+    for seed in range(6 * block, 6 * block + 6):
+        assert F.one_operator_case(seed) is None
