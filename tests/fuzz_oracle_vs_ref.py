@@ -48,7 +48,7 @@ def random_controls(rng, s, multi):
     smoothers = [x for x in cases.SMOOTHERS if cases.selectable(s, x)]
     kind = rng.choice(["krylov", "smooth", "gamg", "krylov_gamg"], p=[0.4, 0.2, 0.3, 0.1])
     tol = float(rng.choice([1e-4, 1e-7, 1e-10]))
-    common = dict(tolerance=tol, relTol=float(rng.choice([0, 0, 0.01])), maxIter=int(rng.choice([3, 40, 1000])))
+    common = dict(tolerance=tol, relTol=float(rng.choice([0, 0, 0.01])), maxIter=int(rng.choice([0, 3, 40, 1000])))
     gamg = dict(smoother=str(rng.choice(smoothers)), agglomerator=str(rng.choice(["algebraicPair", "faceAreaPair"])),
                 nCellsInCoarsestLevel=int(rng.choice([2, 4, 10])), mergeLevels=int(rng.choice([1, 1, 2, 3])),
                 cacheAgglomeration=False, nPreSweeps=int(rng.choice([0, 0, 1, 2])),
@@ -61,7 +61,7 @@ def random_controls(rng, s, multi):
         return dict(common, solver="PBiCG" if asym else "PCG", preconditioner=str(rng.choice(pres)))
     if kind == "smooth":
         return dict(common, solver="smoothSolver", smoother=str(rng.choice(smoothers)),
-                    nSweeps=int(rng.choice([1, 2, 3])))
+                    nSweeps=int(rng.choice([1, 2, 3, -2])))
     if kind == "gamg" or asym:
         return dict(common, solver="GAMG", **gamg)
     return dict(common, solver="PCG", preconditioner=dict(gamg, preconditioner="GAMG", tolerance=1e-4, relTol=0,
@@ -130,6 +130,75 @@ def one_operator_case(seed):
     return None
 
 
+def one_multi_region_operator_case(seed):
+    """operators and smoothers of 2-4 coupled regions (random partition, random cyclic pairs)"""
+    if not O.ref_par_available():
+        return None
+    rng = np.random.default_rng(20_000_000 + seed)
+    s = random_system(rng)
+    if s["nCells"] < 8:
+        return None
+    R = int(rng.integers(2, 5))
+    proc = rng.integers(0, R, s["nCells"]).astype(np.int32)
+    proc[:R] = np.arange(R)
+    regs = decompose.decompose(s, proc, R)
+    for r, reg in enumerate(regs):
+        if reg["nCells"] >= 6 and rng.random() < 0.3:
+            add_random_cyclic(rng, reg, r)
+    w = O.World(regs)
+    x = rng.standard_normal(s["nCells"])
+    xs = [x[r["cells"]] for r in regs]
+    srcs = [r["source"] for r in regs]
+
+    def same(a, b):
+        return all(np.array_equal(p, q) for p, q in zip(a, b))
+
+    for op, mine in (("amul", lambda: w.amul(xs)), ("tmul", lambda: w.tmul(xs)), ("suma", lambda: w.sumA()),
+                     ("residual", lambda: w.residual(xs, srcs))):
+        if not same(mine(), O.ref_run_par(regs, op, psi=xs, timeout=120)[0]):
+            return f"multi-region operator seed {seed}: {op} differs (R={R})"
+    nsw = int(rng.integers(1, 4))
+    for sm in cases.SMOOTHERS:
+        if cases.selectable(s, sm):
+            want = O.ref_run_par(regs, "smooth", O.dict_text(dict(smoother=sm)), nsw, psi=xs, timeout=120)[0]
+            if not same(w.smooth(sm, xs, srcs, nsw), want):
+                return f"multi-region operator seed {seed}: smoother {sm} x{nsw} differs (R={R})"
+    return None
+
+
+def one_cache_case(seed):
+    """two solves with changed coefficients in between, cacheAgglomeration on or off (driver op solve2)"""
+    rng = np.random.default_rng(30_000_000 + seed)
+    s = random_system(rng)
+    if s["nCells"] < 12:
+        return None
+    smoothers = [x for x in cases.SMOOTHERS if cases.selectable(s, x)]
+    ctl = dict(solver="GAMG", smoother=str(rng.choice(smoothers)),
+               agglomerator=str(rng.choice(["algebraicPair", "faceAreaPair"])),
+               nCellsInCoarsestLevel=int(rng.choice([2, 4])), mergeLevels=int(rng.choice([1, 2])),
+               cacheAgglomeration=bool(rng.random() < 0.7), tolerance=1e-8, relTol=0, maxIter=60)
+    w = O.World([s])
+    try:
+        w.solve(ctl, s["psi0"].copy(), s["source"])
+        w.set_coeffs(0, *O.second_coeffs(s))
+        psi2, perf2 = w.solve(ctl, s["psi0"].copy(), s["source"])
+    except AssertionError:
+        psi2 = None
+    try:
+        pr, so = O.ref_run(s, "solve2", O.dict_text(cases.ref_controls(ctl)))
+        ref2 = O.parse_perfs(so)[1]
+    except RuntimeError:
+        pr = None
+    if psi2 is None and pr is None:
+        return None
+    if psi2 is None or pr is None:
+        return f"cache seed {seed}: one side refused {ctl}"
+    if perf2["nIterations"] != ref2["nIterations"] or perf2["finalResidual"] != ref2["finalResidual"] \
+            or not np.array_equal(psi2[0], pr):
+        return f"cache seed {seed}: second solve differs {perf2} vs {ref2} {ctl}"
+    return None
+
+
 def one_case(seed):
     """-> None if oracle and reference agree (or both refuse), else a description of the difference"""
     rng = np.random.default_rng(seed)
@@ -148,6 +217,10 @@ def one_case(seed):
         for r, reg in enumerate(regs):
             if reg["nCells"] >= 6 and rng.random() < 0.25:
                 add_random_cyclic(rng, reg, r)
+    if rng.random() < 0.1:                            # zero source: normFactor is 1e-20 plus |A psi| terms
+        s["source"] = np.zeros(s["nCells"])
+        for r in regs:
+            r["source"] = np.zeros(r["nCells"])
     psis = [psi0[r["cells"]] for r in regs] if R > 1 else [psi0]
     srcs = [r["source"] for r in regs]
     try:
@@ -185,7 +258,9 @@ if __name__ == "__main__":
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     bad = 0
     for k in range(n):
-        for msg in (one_case(seed0 + k), one_operator_case(seed0 + k) if k % 4 == 0 else None):
+        for msg in (one_case(seed0 + k), one_operator_case(seed0 + k) if k % 4 == 0 else None,
+                    one_multi_region_operator_case(seed0 + k) if k % 8 == 1 else None,
+                    one_cache_case(seed0 + k) if k % 8 == 2 else None):
             if msg:
                 bad += 1
                 print(msg, flush=True)

@@ -25,3 +25,17 @@ def test_random_operators_smoothers_and_numberings_agree_with_the_reference(bloc
     import fuzz_oracle_vs_ref as F
     for seed in range(6 * block, 6 * block + 6):
         assert F.one_operator_case(seed) is None
+
+
+@pytest.mark.skipif(not O.ref_par_available(), reason="oracle/_ref (parallel driver) not built")
+def test_random_multi_region_operators_agree_with_the_reference():
+    import fuzz_oracle_vs_ref as F
+    for seed in range(8):
+        assert F.one_multi_region_operator_case(seed) is None
+
+
+def test_random_two_solve_sequences_agree_with_the_reference():
+    """cacheAgglomeration on/off, coefficients changed between the solves"""
+    import fuzz_oracle_vs_ref as F
+    for seed in range(16):
+        assert F.one_cache_case(seed) is None
