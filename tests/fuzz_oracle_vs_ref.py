@@ -16,8 +16,11 @@ from ldub200 import decompose  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
+MAX_CELLS = int(__import__("os").environ.get("FUZZ_MAX_CELLS", "70"))   # larger: deeper GAMG hierarchies
+
+
 def random_system(rng):
-    n = int(rng.integers(1, 70))
+    n = int(rng.integers(1, MAX_CELLS))
     # a spanning chain (so GAMG can agglomerate) plus random extra faces
     pairs = set()
     order = rng.permutation(n)
