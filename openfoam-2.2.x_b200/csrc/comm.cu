@@ -141,6 +141,10 @@ static int halo_grid(ldu_matrix* m, dim3& grid, IfaceDev** tab)
         LDU_TRY(ldu_comm_connect(ctx, handle));
         ctx->comm.selfOnly = true;
     }
+    if (ctx->comm.selfOnly && !allSelf) {
+        set_error("matrix has interfaces to other ranks but the context has no peers (ldu_comm_connect)");
+        return LDU_ECOMM;
+    }
     if ((int)m->ifs.size() > ctx->comm.maxInterfaces || maxN > ctx->comm.slotStride) {
         set_error("exchange window too small for this matrix's interfaces");
         return LDU_ECOMM;
@@ -220,6 +224,15 @@ int ldu_comm_window_create(ldu_context* ctx, int rank, int nRanks, int maxInterf
     static_assert(sizeof(cudaIpcMemHandle_t) <= LDU_COMM_HANDLE_BYTES, "handle size");
     LDU_CUDA(cudaSetDevice(ctx->device));
     Comm& cm = ctx->comm;
+    if (cm.window) {   // a window the library made for cyclic-only matrices, or an earlier call: replace it
+        LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(cm.window);
+        cudaFree(cm.d_peer);
+        cm.window = nullptr;
+        cm.d_peer = nullptr;
+        cm.connected = false;
+    }
+    cm.selfOnly = false;
     cm.rank = rank;
     cm.nRanks = nRanks;
     cm.maxInterfaces = std::max(maxInterfaces, 1);
