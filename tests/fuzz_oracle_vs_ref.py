@@ -181,6 +181,36 @@ def one_multi_region_operator_case(seed):
     return None
 
 
+def one_polymesh_case(seed):
+    """random regions (processor + cyclic patches) -> processorN/constant/polyMesh files -> regions"""
+    import tempfile
+    from ldub200 import polymesh
+    rng = np.random.default_rng(40_000_000 + seed)
+    s = random_system(rng)
+    if s["nCells"] < 8:
+        return None
+    R = int(rng.integers(1, 6))
+    proc = rng.integers(0, R, s["nCells"]).astype(np.int32)
+    proc[:R] = np.arange(R)
+    regs = decompose.decompose(s, proc, R)
+    for r, reg in enumerate(regs):
+        if reg["nCells"] >= 6 and rng.random() < 0.4:
+            add_random_cyclic(rng, reg, r)
+    with tempfile.TemporaryDirectory() as td:
+        polymesh.write_decomposed_case(td, regs)
+        back = polymesh.read_decomposed_case(td)
+    for r, (a, b) in enumerate(zip(back, regs)):
+        if not (np.array_equal(a["lower"], b["lower"]) and np.array_equal(a["upper"], b["upper"])):
+            return f"polymesh seed {seed}: addressing of region {r} differs"
+        if [(i["nbrRegion"], i["nbrInterface"]) for i in a["interfaces"]] != \
+                [(i["nbrRegion"], i["nbrInterface"]) for i in b["interfaces"]]:
+            return f"polymesh seed {seed}: interface table of region {r} differs"
+        for x, y in zip(a["interfaces"], b["interfaces"]):
+            if not np.array_equal(x["faceCells"], y["faceCells"]):
+                return f"polymesh seed {seed}: faceCells of region {r} differ"
+    return None
+
+
 def one_cache_case(seed):
     """two solves with changed coefficients in between, cacheAgglomeration on or off (driver op solve2)"""
     rng = np.random.default_rng(30_000_000 + seed)
@@ -275,7 +305,8 @@ if __name__ == "__main__":
     for k in range(n):
         for msg in (one_case(seed0 + k), one_operator_case(seed0 + k) if k % 2 == 0 else None,
                     one_multi_region_operator_case(seed0 + k) if k % 8 == 1 else None,
-                    one_cache_case(seed0 + k) if k % 8 == 2 else None):
+                    one_cache_case(seed0 + k) if k % 8 == 2 else None,
+                    one_polymesh_case(seed0 + k) if k % 4 == 3 else None):
             if msg:
                 bad += 1
                 print(msg, flush=True)

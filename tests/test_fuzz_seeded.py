@@ -39,3 +39,9 @@ def test_random_two_solve_sequences_agree_with_the_reference():
     import fuzz_oracle_vs_ref as F
     for seed in range(16):
         assert F.one_cache_case(seed) is None
+
+
+def test_random_regions_survive_the_polymesh_round_trip():
+    import fuzz_oracle_vs_ref as F
+    for seed in range(60):
+        assert F.one_polymesh_case(seed) is None
