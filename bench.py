@@ -106,10 +106,17 @@ def reference_cores():
     """Host cores the reference arm uses: the reference is single-threaded per rank, so the arm
     runs it the way OpenFOAM is run on a multi-core host — the box decomposed into one mesh region
     per core, one reference process per region, coupled through processor interfaces — on up to
-    8 cores.  This image has no MPI: the reference's Pstream seam is served by
+    32 cores, all the host offers.  This image has no MPI: the reference's Pstream seam is served by
     oracle/pstream_shm (shared memory) instead of src/Pstream/mpi."""
-    c = os.cpu_count() or 1
-    return 8 if c >= 8 else 4 if c >= 4 else 2 if c >= 2 else 1
+    try:
+        c = len(os.sched_getaffinity(0))
+    except Exception:
+        c = os.cpu_count() or 1
+    c = int(os.environ.get("LDU_REF_CORES", c))
+    for k in (32, 16, 8, 4, 2):       # the region counts ldub200.decompose.split_for knows
+        if c >= k:
+            return k
+    return 1
 
 
 def reference_mode(cores):
@@ -151,14 +158,19 @@ def reference_rate(n, precond, it_a, it_b, keep=None, cores=None):
         return (ib - ia) / (tb - ta) if tb - ta > 0.25 * tb else ib / max(tb, 1e-9)
 
     if reference_mode(cores) == "coupled":
-        _, so = O.ref_run_par(blocks, "time_iters", ctl, it_a - 1, it_b - 1)
+        out, so = O.ref_run_par(blocks, "time_iters", ctl, it_a - 1, it_b - 1)
         ia, ta, ib, tb = iters_line(so)
+        if keep is not None:
+            keep["last"] = dict(perf=O.parse_perfs(so)[-1], psi=out)
         return rate(ia, ta, ib, tb), "reference", (tb + ta) * cores, cores
 
     def one(s):
         if O.ref_available():
-            ia, ta, ib, tb = iters_line(O.ref_run({k: v for k, v in s.items() if k != "interfaces"},
-                                                  "time_iters", ctl, it_a - 1, it_b - 1)[1])
+            out, so = O.ref_run({k: v for k, v in s.items() if k != "interfaces"},
+                                "time_iters", ctl, it_a - 1, it_b - 1)
+            ia, ta, ib, tb = iters_line(so)
+            if keep is not None and cores == 1:
+                keep["last"] = dict(perf=O.parse_perfs(so)[-1], psi=[out])
             return rate(ia, ta, ib, tb), "reference", tb + ta
         # restatement (oracle/ldu_oracle.c) when the compiled reference did not travel
         s = {k: v for k, v in s.items() if k != "interfaces"}
@@ -173,6 +185,19 @@ def reference_rate(n, precond, it_a, it_b, keep=None, cores=None):
     with ThreadPoolExecutor(max_workers=cores) as ex:
         res = list(ex.map(one, blocks))
     return min(r[0] for r in res), res[0][1], sum(r[2] for r in res), cores
+
+
+def workload_name(n, precond):
+    """config.workload: the SAME string in both arms (how each arm cuts the mesh is config.decomposition)"""
+    return f"box{n} PCG+{precond}, {n**3} cells"
+
+
+def decomposition_name(regions, what):
+    from ldub200 import decompose
+    px, py, pz = decompose.split_for(regions)
+    if regions == 1:
+        return f"undecomposed (1 region, global DIC), {what}"
+    return f"{px}x{py}x{pz} blocks = {regions} regions, processor-patch halos + global sums, block-local DIC, {what}"
 
 
 def reference_sample(n, precond, iters, cores):
@@ -207,12 +232,16 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ref_iters / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"box{args.n} PCG+{args.precond}, {args.n**3} cells", "precond": args.precond,
-                   "timing": "reference clockTime"},
+        "config": {"workload": workload_name(args.n, args.precond), "precond": args.precond,
+                   "decomposition": decomposition_name(cores, f"one reference process per region on {cores} host cores"),
+                   "iters_per_step": args.ref_iters, "timing": "reference clockTime"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if "last" in keep:
+        line["final_residual"] = {"iterations": keep["last"]["perf"]["nIterations"],
+                                  "value": keep["last"]["perf"]["finalResidual"]}
     print(json.dumps(line))
 
 
@@ -277,10 +306,13 @@ def run_ours(args):
         return ms
 
     # ---- device-resident solve --------------------------------------------------
+    last = {}
+
     def step_device():
         d_psi.zero()
         perf = solver.solve_device(d_psi, d_src)
         assert perf.nIterations == args.iters, str(perf)
+        last["perf"] = perf
 
     for _ in range(args.warmup):
         step_device()
@@ -291,6 +323,21 @@ def run_ours(args):
     ms = timed(step_device, args.steps)
     launches = ldub200.launch_count() - l0
     value = args.steps * args.iters / (ms * 1e-3)
+
+    final_residual = last["perf"].finalResidual
+    psi_dev = d_psi.download()       # psi of the last timed step (this rank's region)
+
+    # ---- the HBM-bound curve beside it: the same solve with the diagonal preconditioner ------------
+    solver_diag = ldub200.lduMatrix.solver.New("p", A, controls("diagonal", args.iters))
+
+    def step_diag():
+        d_psi.zero()
+        solver_diag.solve_device(d_psi, d_src)
+
+    for _ in range(3):
+        step_diag()
+    ms_diag = timed(step_diag, args.steps)
+    value_diag = args.steps * args.iters / (ms_diag * 1e-3)
 
     # ---- Amul alone (roofline) ------------------------------------------------------
     d_src2 = ldub200.DeviceField(ctx, nC, np.sin(0.11 * np.arange(nC)))
@@ -349,7 +396,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"box{n} PCG+{args.precond}, {n**3} cells, {world} region(s)",
+        "config": {"workload": workload_name(n, args.precond),
+                   "decomposition": decomposition_name(world, "one region per B200"),
                    "precond": args.precond, "iters_per_step": args.iters,
                    "l2": "inputs larger than L2 (0.72 GB per Amul), no flush",
                    "pcg_alg_bytes_per_cell_iter": 352 if args.precond == "DIC" else 208},
@@ -370,6 +418,11 @@ def run_ours(args):
                                   if args.precond == "DIC" else "hbm"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
+        "pcg_diagonal": {"value": value_diag, "unit": UNIT, "ms_per_step": ms_diag / args.steps,
+                         "alg_bytes_per_cell_iter": 208,
+                         "frac_of_hbm_peak": value_diag * 208 * n ** 3 / 1e9 / world / peak,
+                         "note": "same solve with `preconditioner diagonal`: no dependency chain, the HBM-bound "
+                                 "curve of the PCG loop (Amul + fused BLAS-1 kernels)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -382,10 +435,43 @@ def run_ours(args):
         except Exception:
             pass
 
+    # ---- parity: the unmodified reference on the SAME decomposition, the same number of iterations ----
+    if not args.no_parity:
+        par = None
+        if rank == 0:
+            try:
+                from oracle import oracle as O
+                keep = {}
+                t0 = time.perf_counter()
+                rate1, kind, _, _ = reference_rate(n, args.precond, 2, args.iters, keep, cores=world)
+                pr = keep["last"]["perf"]
+                psi_ref = keep["last"]["psi"][0]
+                par = {"mode": "default (fixed-shape tree sums; referenceOrderSums off), the timed configuration",
+                       "reference": f"oracle/_ref ({kind}), {world} region(s), same decomposition, "
+                                    f"{pr['nIterations']} iterations",
+                       "iterations": [int(last["perf"].nIterations), int(pr["nIterations"])],
+                       "iterations_equal": bool(last["perf"].nIterations == pr["nIterations"]),
+                       "final_residual": final_residual, "reference_final_residual": pr["finalResidual"],
+                       "rel_diff_final_residual": abs(final_residual - pr["finalResidual"]) / pr["finalResidual"],
+                       "max_rel_diff_psi_region0": float(np.abs(psi_dev - psi_ref).max() / np.abs(psi_ref).max()),
+                       "exact_mode": "referenceOrderSums on is bit-identical at this size "
+                                     "(tests/test_gpu_parity_fullsize.py)",
+                       "reference_rate_same_decomposition": rate1,
+                       "seconds": time.perf_counter() - t0}
+            except Exception as e:
+                par = {"failed": str(e)[:300]}
+        if dist is not None:
+            dist.barrier()
+        if rank == 0:
+            line["parity"] = par
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             v, kind, spent, cores = reference_rate(n, args.precond, 2, 2 + args.ref_iters)
-            v1, _, spent1, _ = reference_rate(n, args.precond, 2, 2 + args.ref_iters, cores=1)
+            if line.get("parity") and "reference_rate_same_decomposition" in line["parity"]:
+                v1, spent1 = line["parity"]["reference_rate_same_decomposition"], line["parity"]["seconds"]
+            else:
+                v1, _, spent1, _ = reference_rate(n, args.precond, 2, 2 + args.ref_iters, cores=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": reference_sample(n, args.precond, args.ref_iters, cores)
                                               + f" ({spent:.1f} s of CPU work)",
@@ -412,7 +498,8 @@ def main():
     ap.add_argument("--n", type=int, default=216, help="box edge (216 -> 10,077,696 cells)")
     ap.add_argument("--precond", default="DIC")
     ap.add_argument("--iters", type=int, default=50, help="PCG iterations per step")
-    ap.add_argument("--ref-iters", type=int, default=8, help="reference iterations timed per step")
+    ap.add_argument("--ref-iters", type=int, default=50, help="reference iterations timed per step")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference run behind the parity object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -93,6 +93,7 @@ def library():
         L.ldu_tmul.argtypes = [vp, vp, vp]
         L.ldu_sumA.argtypes = [vp, vp]
         L.ldu_colour_order.argtypes = [i, i, vp, vp, vp, vp]
+        L.ldu_band_compression.argtypes = [i, i, vp, vp, vp]
         L.ldu_H.argtypes = [vp, vp, vp]
         L.ldu_H1.argtypes = [vp, vp]
         L.ldu_faceH.argtypes = [vp, vp, vp]

@@ -27,8 +27,9 @@ def block_partition(nx, ny, nz, px, py, pz):
 
 
 def split_for(n_ranks: int):
-    """block counts (px, py, pz) used for 1/2/4/8 ranks (2x1x1, 2x2x1, 2x2x2)."""
-    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n_ranks]
+    """block counts (px, py, pz) used for 1/2/4/8 ranks (2x1x1, 2x2x1, 2x2x2); 16 and 32 regions
+    (2x2x4, 2x4x4: the cuts go where the lexicographic numbering is coarsest) serve the many-core CPU arm."""
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2), 16: (2, 2, 4), 32: (2, 4, 4)}[n_ranks]
 
 
 def decompose(sysd: dict, proc: np.ndarray, n_regions: int):

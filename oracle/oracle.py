@@ -387,7 +387,7 @@ def ref_run(sysd, op, *args, psi=None, source=None, ints=False, timeout=3600, ex
 
 
 REF_DRIVER_PAR = HERE / "_ref" / "ref_driver_par"
-_SHM_WORLD_BYTES = 300 << 20     # >= sizeof(lduShm::World) (oracle/pstream_shm/shmWorld.H); sparse
+_SHM_WORLD_BYTES = 1100 << 20    # >= sizeof(lduShm::World) (oracle/pstream_shm/shmWorld.H); sparse
 
 
 def ref_par_available() -> bool:
