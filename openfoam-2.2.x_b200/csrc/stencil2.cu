@@ -78,7 +78,21 @@ struct Box2 {
     int steps;   // nx + 31 skewed steps per tile
     int nTiles;  // nz * nJ
     int nKg;     // k-groups of W planes
+    int W3;      // 0: tile layout [tile][step][lane]; > 0: stacked layout of the register-stacked sweeps, see tile_row
+    int ticks;   // stacked layout: steps + W3 - 1 ticks per (stack, column) group
 };
+
+// Row (32 doubles) of step t of the tile (plane k, column J).
+//   tile layout    : [k][J][t]
+//   stacked layout : [kg = k / W][J][tick = t + p][p = k % W] -- the W rows one warp of sweep3_kernel
+//     needs in one tick (plane p of the stack lags p steps behind plane 0) are adjacent: 256*W bytes per
+//     operand and tick, one contiguous stream per (stack, column) group in both sweep directions.
+__device__ __forceinline__ long long tile_row(const Box2& b, int k, int J, int t)
+{
+    if (b.W3 == 0) return (long long)(k * b.nJ + J) * b.steps + t;
+    const int kg = k / b.W3, p = k - kg * b.W3;
+    return ((long long)(kg * b.nJ + J) * b.ticks + (t + p)) * b.W3 + p;
+}
 
 __device__ __forceinline__ void g_store(LLW* p, double v, unsigned int tag)
 {
@@ -463,6 +477,220 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Third generation: REGISTER-STACKED planes (LDU_STENCIL=3, the default).
+//
+// What bounded sweep2_kernel was the tick: W warps of a CTA meeting at a named barrier once per
+// step and handing a 256-byte row to the next plane through shared memory (~470 cycles per tick
+// measured, ~1200 with the CTA-to-CTA hops).  Here ONE WARP owns the whole stack: W consecutive
+// k-planes of a 32-line column live in the registers of the same lanes (res[p] = result of plane p
+// in the previous tick), so
+//   * the k-neighbour of plane p is the register res[p-1] of the same lane (no shared memory, no barrier),
+//   * the j-neighbour is one shuffle, the i-neighbour the lane's own register,
+//   * the W planes of a tick are W independent dependency chains (mul, sub, shuffle, mul, sub, mul, sub): the
+//     FP64 pipe stays busy without any other warp,
+//   * nothing in the CTA synchronises: a CTA is one warp.
+// Operands arrive through a cp.async ring (kD3 ticks deep) from the STACKED layout (tile_row): the 4 x W
+// rows of a tick are 4 contiguous blocks of 256 W bytes.  Only the faces of a (stack, column) group cross
+// CTAs, as {value, epoch} words polled in L2 kA3 ticks ahead of their use:
+//   gK[group][step][lane]      the last plane of the stack below (above, backward sweep)
+//   gJ[group][i + p][p]        the edge line of the previous (next) column, one 16 W-byte row per tick
+// Groups are claimed from an atomic ticket in dependency order (no co-residency requirement).
+// Arithmetic and its order are those of sweep2_kernel: bit-identical to the reference.
+// ---------------------------------------------------------------------------
+constexpr int kD3 = 6;    // operand ring depth (ticks)
+constexpr int kA3 = 4;    // look-ahead of the polled words (ticks) = unroll factor of the tick loop
+
+__device__ __forceinline__ void cp_async16(unsigned int dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int W, bool BWD>
+__global__ void __launch_bounds__(32) sweep3_kernel(S2Args a)
+{
+    extern __shared__ uint4 smem_raw[];
+    if (a.guarded && a.S->done) return;
+    const int lane = threadIdx.x;
+    int tk = 0;
+    if (lane == 0) tk = (int)atomicAdd(&a.ticket[0], 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+
+    const int nx = a.b.nx, nJ = a.b.nJ, steps = a.b.steps, ticks = a.b.ticks, nKg = a.b.nKg;
+    const int nCta = nKg * nJ;
+    const int tr = BWD ? nCta - 1 - tk : tk;
+    const int kg = tr / nJ, J = tr - kg * nJ;
+    const int g = kg * nJ + J;
+    const int Wg = min(W, a.b.nz - kg * W);                    // planes of this stack that exist
+    const bool kIn = BWD ? (kg + 1 < nKg) : (kg > 0);
+    const bool kOut = BWD ? (kg > 0) : (kg + 1 < nKg);
+    const bool jIn = BWD ? (J + 1 < nJ) : (J > 0);
+    const bool jOut = BWD ? (J > 0) : (J + 1 < nJ);
+    const unsigned int epoch = a.epoch;
+    const int nRho = nx + W - 1;                               // rows of a group's gJ block
+    const long long elemBase = (long long)g * ticks * W * 32;  // first element of the group's stream
+    const double* pOp[4] = {a.pk + elemBase, a.pj + elemBase, a.pi + elemBase, a.Y + elemBase};
+    double* pY = a.Y + elemBase + lane;
+    const LLW* gKin = a.gK + ((long long)(BWD ? g + nJ : g - nJ) * steps) * 32 + lane;
+    LLW* gKout = a.gK + ((long long)g * steps) * 32 + lane;
+    const LLW* gJin = a.gJ + ((long long)(BWD ? g + 1 : g - 1) * nRho) * W + (lane < W ? lane : 0);
+    LLW* gJout = a.gJ + ((long long)g * nRho) * W;
+    const unsigned int ring = (unsigned int)__cvta_generic_to_shared(smem_raw);
+    constexpr unsigned int kOpBytes = W * 256u, kSlotBytes = 4u * kOpBytes;
+    const int edgeLane = BWD ? 31 : 0, pubLane = BWD ? 0 : 31;
+
+    // loop tick s -> layout tick
+    auto sigma_of = [&](int s_) { return BWD ? ticks - 1 - s_ : s_; };
+    auto issue = [&](int s_, unsigned int slot) {
+        if (s_ < ticks) {
+            const long long e = (long long)sigma_of(s_) * (W * 32);
+            const unsigned int d = ring + slot * kSlotBytes + (unsigned int)lane * 16u;
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                const double* src = pOp[o] + e + lane * 2;
+#pragma unroll
+                for (int c = 0; c < W / 2; c++) cp_async16(d + o * kOpBytes + c * 512u, src + c * 64);
+            }
+        }
+        cp_async_commit();
+    };
+    // rows of the polled words of loop tick s_ (negative: none)
+    auto k_row = [&](int s_) -> int {
+        if (!kIn || s_ >= ticks) return -1;
+        const int sg = sigma_of(s_);
+        const int t = BWD ? sg - (W - 1) : sg;
+        return (t >= 0 && t < steps) ? t : -1;
+    };
+    auto j_row = [&](int s_) -> int {
+        if (!jIn || s_ >= ticks) return -1;
+        const int sg = sigma_of(s_);
+        const int rho = BWD ? sg - 31 : sg;
+        return (rho >= 0 && rho < nRho) ? rho : -1;
+    };
+    LLW wk[kA3], wj[kA3];
+    auto peek = [&](int s_, LLW& k_, LLW& j_) {
+        const int kr = k_row(s_), jr = j_row(s_);
+        if (kr >= 0) g_peek(gKin + (long long)kr * 32, k_);
+        if (jr >= 0 && lane < W) g_peek(gJin + (long long)jr * W, j_);
+    };
+    bool dead = false;
+    auto wait_k = [&](int kr, LLW& w) {     // all 32 words of the row
+        long long t0c = 0;
+        while (!dead && !__all_sync(0xffffffffu, ok(w, epoch))) {
+            g_peek(gKin + (long long)kr * 32, w);
+            if (t0c == 0) t0c = clock64();
+            else if (clock64() - t0c > kTimeout2) dead = true;
+            dead = __any_sync(0xffffffffu, dead);
+        }
+    };
+    auto wait_j = [&](int jr, LLW& w) {     // the W words of the row, one per lane < W
+        long long t0c = 0;
+        while (!dead && !__all_sync(0xffffffffu, lane >= W || ok(w, epoch))) {
+            if (lane < W) g_peek(gJin + (long long)jr * W, w);
+            if (t0c == 0) t0c = clock64();
+            else if (clock64() - t0c > kTimeout2) dead = true;
+            dead = __any_sync(0xffffffffu, dead);
+        }
+    };
+
+    double res[W];
+#pragma unroll
+    for (int p = 0; p < W; p++) res[p] = 0.0;
+#pragma unroll
+    for (int q = 0; q < kD3; q++) issue(q, (unsigned int)q);
+#pragma unroll
+    for (int q = 0; q < kA3; q++) {
+        wk[q].f0 = wk[q].f1 = wj[q].f0 = wj[q].f1 = epoch - 1u;
+        wk[q].lo = wk[q].hi = wj[q].lo = wj[q].hi = 0u;
+        peek(q, wk[q], wj[q]);
+    }
+
+    unsigned int slot = 0;
+    for (int sb = 0; sb < ticks; sb += kA3) {
+#pragma unroll
+        for (int q = 0; q < kA3; q++) {
+            const int s_ = sb + q;
+            if (s_ < ticks) {
+                const int sg = sigma_of(s_);
+                // ---- faces of the group: words published by the CTAs of the neighbouring groups
+                double vkin = 0.0, ev = 0.0;
+                const int kr = k_row(s_), jr = j_row(s_);
+                if (kr >= 0) {
+                    if (!__all_sync(0xffffffffu, ok(wk[q], epoch))) wait_k(kr, wk[q]);
+                    vkin = val(wk[q]);
+                }
+                if (jr >= 0) {
+                    if (!__all_sync(0xffffffffu, lane >= W || ok(wj[q], epoch))) wait_j(jr, wj[q]);
+                    ev = val(wj[q]);
+                }
+                // ---- operands of this tick have landed
+                cp_async_wait<kD3 - 1>();
+                __syncwarp();
+                const unsigned int d = ring + slot * kSlotBytes + (unsigned int)lane * 8u;
+                // ---- W planes, each one step: res[p] <- src - pk*vk - pj*vj - pi*res[p]
+#pragma unroll
+                for (int pp = 0; pp < W; pp++) {
+                    const int p = BWD ? pp : W - 1 - pp;        // consume the old value of the plane it depends on
+                    const double opk = lds64(d + p * 256u);
+                    const double opj = lds64(d + kOpBytes + p * 256u);
+                    const double opi = lds64(d + 2u * kOpBytes + p * 256u);
+                    const double src = lds64(d + 3u * kOpBytes + p * 256u);
+                    const double vk = BWD ? (p < W - 1 ? res[p < W - 1 ? p + 1 : p] : vkin)
+                                          : (p > 0 ? res[p > 0 ? p - 1 : p] : vkin);
+                    double vj = BWD ? __shfl_down_sync(0xffffffffu, res[p], 1) : __shfl_up_sync(0xffffffffu, res[p], 1);
+                    if (jIn) {
+                        const double e = __shfl_sync(0xffffffffu, ev, p);
+                        if (lane == edgeLane) vj = e;
+                    }
+                    double acc = __dsub_rn(src, __dmul_rn(opk, vk));
+                    acc = __dsub_rn(acc, __dmul_rn(opj, vj));
+                    acc = __dsub_rn(acc, __dmul_rn(opi, res[p]));
+                    res[p] = acc;
+                }
+                // ---- results: the vector itself, then the faces other groups wait for
+#pragma unroll
+                for (int p = 0; p < W; p++) {
+                    const int t = sg - p;
+                    if (t >= 0 && t < steps && p < Wg) pY[((long long)sg * W + p) * 32] = res[p];
+                }
+                if (kOut) {
+                    const int t = BWD ? sg : sg - (W - 1);
+                    if (t >= 0 && t < steps) g_store(gKout + (long long)t * 32, BWD ? res[0] : res[W - 1], epoch);
+                }
+                if (jOut) {
+                    const int rho = BWD ? sg : sg - 31;
+                    if (rho >= 0 && rho < nRho && lane == pubLane) {
+#pragma unroll
+                        for (int p = 0; p < W; p++) g_store(gJout + (long long)rho * W + p, res[p], epoch);
+                    }
+                }
+                // ---- refill: this tick's ring slot, and the words of tick s + kA3
+                __syncwarp();
+                issue(s_ + kD3, slot);
+                slot = slot + 1u == (unsigned int)kD3 ? 0u : slot + 1u;
+                wk[q].f0 = wk[q].f1 = wj[q].f0 = wj[q].f1 = epoch - 1u;
+                peek(s_ + kA3, wk[q], wj[q]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (dead && lane == 0) {
+        a.S->commError = 2;
+        a.S->done = 1;
+    }
+    // the last CTA re-arms the ticket for the next launch
+    if (lane == 0) {
+        __threadfence();
+        const unsigned int doneCtas = atomicAdd(&a.ticket[1], 1u);
+        if (doneCtas == (unsigned int)nCta - 1u) {
+            a.ticket[0] = 0u;
+            a.ticket[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // natural cell order <-> tile layout, 32 steps x 32 lines per CTA through shared memory
 // ---------------------------------------------------------------------------
@@ -488,7 +716,7 @@ __global__ void __launch_bounds__(256) pack2_kernel(Box2 b, int nBlk, const doub
     __syncthreads();
     for (int x = wid; x < 32; x += 8) {
         const int t = tb + x;
-        if (t < b.steps) Y[((long long)T * b.steps + t) * 32 + lane] = s[lane][x];
+        if (t < b.steps) Y[tile_row(b, k, J, t) * 32 + lane] = s[lane][x];
     }
 }
 
@@ -503,7 +731,7 @@ __global__ void __launch_bounds__(256) unpack2_kernel(Box2 b, int nBlk, const do
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int x = wid; x < 32; x += 8) {
         const int t = tb + x;
-        s[lane][x] = (t < b.steps) ? Y[((long long)T * b.steps + t) * 32 + lane] : 0.0;
+        s[lane][x] = (t < b.steps) ? Y[tile_row(b, k, J, t) * 32 + lane] : 0.0;
     }
     __syncthreads();
     for (int r = wid; r < 32; r += 8) {
@@ -528,7 +756,7 @@ __global__ void __launch_bounds__(kBlock) unpack2_dot_kernel(Box2 b, int nBlk, i
         const int k = T / b.nJ, J = T - k * b.nJ;
         for (int x = wid; x < 32; x += 8) {
             const int t = tb + x;
-            s[lane][x] = (t < b.steps) ? Y[((long long)T * b.steps + t) * 32 + lane] : 0.0;
+            s[lane][x] = (t < b.steps) ? Y[tile_row(b, k, J, t) * 32 + lane] : 0.0;
         }
         __syncthreads();
         for (int r = wid; r < 32; r += 8) {
@@ -577,7 +805,7 @@ __global__ void __launch_bounds__(kBlock) xr_pack2_kernel(Box2 b, int nBlk, int 
         __syncthreads();
         for (int x = wid; x < 32; x += 8) {
             const int t = tb + x;
-            if (t < b.steps) Y[((long long)T * b.steps + t) * 32 + lane] = s[lane][x];
+            if (t < b.steps) Y[tile_row(b, k, J, t) * 32 + lane] = s[lane][x];
         }
         __syncthreads();
     }
@@ -638,7 +866,7 @@ __global__ void __launch_bounds__(256) products2_kernel(Box2 b, int nBlk, const 
     for (int x = wid; x < 32; x += 8) {
         const int t = tb + x;
         if (t < b.steps) {
-            const long long p = ((long long)T * b.steps + t) * 32 + lane;
+            const long long p = tile_row(b, k, J, t) * 32 + lane;
             o0[p] = s[0][lane][x];
             o1[p] = s[1][lane][x];
             o2[p] = s[2][lane][x];
@@ -703,6 +931,25 @@ int pick_W(int nz)
     return nz >= 12 ? 6 : 4;
 }
 
+// 2: plane-stacked CTAs (sweep2_kernel), 3 (default): register-stacked warps (sweep3_kernel)
+int box_generation()
+{
+    const char* e = getenv("LDU_STENCIL");
+    return (e && atoi(e) == 2) ? 2 : 3;
+}
+
+// planes per warp of the register-stacked sweeps: the chain of stack-to-stack hops costs
+// nz/W * (W ticks + hop latency), a tick costs ~W * 12 ns: W = 8 is the minimum for 0.5-1 us hops
+int pick_W3(int nz)
+{
+    const char* e = getenv("LDU_STENCIL_W");
+    if (e) {
+        const int w = atoi(e);
+        if (w == 4 || w == 8 || w == 12 || w == 16) return w;
+    }
+    return nz >= 16 ? 8 : 4;
+}
+
 int state2(ldu_matrix* m, State2** out)
 {
     State2* s = reinterpret_cast<State2*>(m->stencil2);
@@ -716,12 +963,16 @@ int state2(ldu_matrix* m, State2** out)
         b.nJ = (b.ny + 31) / 32;
         b.steps = b.nx + 31;
         b.nTiles = b.nz * b.nJ;
-        s->W = pick_W(b.nz);
+        const bool v3 = box_generation() == 3;
+        s->W = v3 ? pick_W3(b.nz) : pick_W(b.nz);
         b.nKg = (b.nz + s->W - 1) / s->W;
-        s->padded = (long long)b.nTiles * b.steps * 32;
+        b.W3 = v3 ? s->W : 0;
+        b.ticks = b.steps + s->W - 1;
+        s->padded = v3 ? (long long)b.nKg * b.nJ * b.ticks * s->W * 32 : (long long)b.nTiles * b.steps * 32;
         cudaStream_t st = m->ctx->stream;
         LDU_TRY(alloc_padded2((void**)&s->Y, (size_t)s->padded, sizeof(double), st));
-        const size_t nK = (size_t)b.nKg * b.nJ * b.steps * 32, nJw = (size_t)b.nTiles * b.steps;
+        const size_t nK = (size_t)b.nKg * b.nJ * b.steps * 32;
+        const size_t nJw = v3 ? (size_t)b.nKg * b.nJ * (b.nx + s->W - 1) * s->W : (size_t)b.nTiles * b.steps;
         LDU_CUDA(cudaMalloc((void**)&s->gK, nK * sizeof(LLW)));
         LDU_CUDA(cudaMemsetAsync(s->gK, 0, nK * sizeof(LLW), st));
         LDU_CUDA(cudaMalloc((void**)&s->gJ, nJw * sizeof(LLW)));
@@ -825,14 +1076,45 @@ int launch_sweeps(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
     return LDU_OK;
 }
 
+template <int W>
+int launch_sweeps3(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
+{
+    const size_t smem = (size_t)kD3 * 4 * W * 256;
+    if (!s->attrSet) {
+        LDU_CUDA(cudaFuncSetAttribute(sweep3_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LDU_CUDA(cudaFuncSetAttribute(sweep3_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s->attrSet = true;
+    }
+    const int grid = s->b.nKg * s->b.nJ;
+    cudaStream_t st = m->ctx->stream;
+    a.trace = nullptr;
+    a.epoch = ++s->epoch;
+    a.pk = P.F[0];
+    a.pj = P.F[1];
+    a.pi = P.F[2];
+    sweep3_kernel<W, false><<<grid, 32, smem, st>>>(a);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    a.epoch = ++s->epoch;
+    a.pk = P.B[0];
+    a.pj = P.B[1];
+    a.pi = P.B[2];
+    sweep3_kernel<W, true><<<grid, 32, smem, st>>>(a);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
 }  // namespace
 
 int stencil_version(const ldu_matrix* m)
 {
     if (m->box[0] <= 0 || !flow_enabled()) return 0;
-    const char* e = getenv("LDU_STENCIL");   // 0: generic dataflow sweeps, 1: stencil.cu, 2 (default): stencil2.cu
-    const int ver = e ? atoi(e) : 2;
-    return (ver < 0 || ver > 2) ? 2 : ver;
+    // 0: generic dataflow sweeps, 1: stencil.cu, 2: stencil2.cu with plane-stacked CTAs,
+    // 3 (default): stencil2.cu with register-stacked warps; 2 and 3 share every entry point
+    const char* e = getenv("LDU_STENCIL");
+    const int ver = e ? atoi(e) : 3;
+    return (ver < 0 || ver >= 2) ? 2 : ver;
 }
 
 void stencil2_free(ldu_matrix* m)
@@ -887,7 +1169,11 @@ static int apply_core(ldu_matrix* m, const double* rD, const double* coefF, cons
     a.gK = s->gK;
     a.gJ = s->gJ;
     a.ticket = s->ticket;
-    if (s->W == 16) LDU_TRY(launch_sweeps<16>(m, s, a, P));
+    if (s->b.W3 == 16) LDU_TRY(launch_sweeps3<16>(m, s, a, P));
+    else if (s->b.W3 == 12) LDU_TRY(launch_sweeps3<12>(m, s, a, P));
+    else if (s->b.W3 == 8) LDU_TRY(launch_sweeps3<8>(m, s, a, P));
+    else if (s->b.W3 == 4) LDU_TRY(launch_sweeps3<4>(m, s, a, P));
+    else if (s->W == 16) LDU_TRY(launch_sweeps<16>(m, s, a, P));
     else if (s->W == 15) LDU_TRY(launch_sweeps<15>(m, s, a, P));
     else if (s->W == 8) LDU_TRY(launch_sweeps<8>(m, s, a, P));
     else if (s->W == 6) LDU_TRY(launch_sweeps<6>(m, s, a, P));

@@ -108,15 +108,17 @@ def test_smoothers_bit_exact(ctx, system, sm):
     A.destroy()
 
 
-@pytest.mark.parametrize("W", ["4", "8", "15", "16"])
-@pytest.mark.parametrize("version", ["1", "2"])
+@pytest.mark.parametrize("W", ["4", "8", "12", "15", "16"])
+@pytest.mark.parametrize("version", ["1", "2", "3"])
 def test_box_sweeps_all_stack_heights(ctx, W, version, monkeypatch):
-    """Structured-box sweeps with every stack height (planes per CTA) and both kernel
+    """Structured-box sweeps with every stack height (planes per CTA / per warp) and all three kernel
     generations: DIC and DILU applications stay bit-identical to the reference order.
-    40 planes: 10 / 5 / 3 / 3 stacks, the last one ragged; 70 lines: 3 columns, ragged."""
+    40 planes: 10 / 5 / 4 / 3 / 3 stacks, the last one ragged; 70 lines: 3 columns, ragged."""
     import ldub200
     if version == "1" and W != "4":
-        pytest.skip("stack height only exists in the second generation")
+        pytest.skip("stack height only exists in the second and third generation")
+    if (version == "2" and W == "12") or (version == "3" and W == "15"):
+        pytest.skip("not a stack height of this generation")
     monkeypatch.setenv("LDU_STENCIL_W", W)
     monkeypatch.setenv("LDU_STENCIL", version)
     O = _oracle()
@@ -241,25 +243,27 @@ def test_solver_performance_print_format(ctx):
 
 
 def test_full_size_box_sweeps_match_generic_path(ctx, monkeypatch):
-    """BASELINE's 10M-cell box (216^3): the plane-stacked sweeps (36 stacks x 7 columns of CTAs) and the
-    generic dataflow sweeps are two independent implementations of the same DIC application; at full size,
-    where the oracle is too slow, they must agree bit for bit, and M w = r must hold for the result."""
+    """BASELINE's 10M-cell box (216^3): the register-stacked sweeps (27 stacks x 7 columns of warps), the
+    plane-stacked sweeps (36 stacks x 7 columns of CTAs) and the generic dataflow sweeps are three independent
+    implementations of the same DIC application and must agree bit for bit (the comparison with the reference
+    itself at this size is tests/test_gpu_parity_fullsize.py)."""
     import ldub200
     n = 216
     s = meshes.laplacian_system(n, n, n, variable=True)
     r = np.sin(0.37 * np.arange(s["nCells"]))
     out = {}
-    for ver in ("2", "0"):
+    for ver in ("3", "2", "0"):
         monkeypatch.setenv("LDU_STENCIL", ver)
         A = _matrix(ctx, s)
         P = ldub200.lduMatrix.preconditioner.New(A, "DIC")
         out[ver] = P.precondition(r)
-        if ver == "2":
+        if ver != "0":
             again = P.precondition(r)      # rings, tickets and epochs are reused
             assert np.array_equal(again, out[ver])
         A.destroy()
-    assert np.array_equal(out["2"], out["0"])
-    assert np.isfinite(out["2"]).all() and np.abs(out["2"]).max() > 0
+    assert np.array_equal(out["3"], out["0"])     # register-stacked warps (the default)
+    assert np.array_equal(out["2"], out["0"])     # plane-stacked CTAs
+    assert np.isfinite(out["3"]).all() and np.abs(out["3"]).max() > 0
 
 
 def test_large_box_properties(ctx):
