@@ -224,6 +224,35 @@ int ldu_solve_device(ldu_matrix* m, const ldu_controls* controls, double* d_psi,
  * (entry 0 = initial); returns the number of entries written */
 int ldu_residual_history(ldu_matrix* m, double* hist, int capacity);
 
+/* ---- GAMG hierarchy built by the host ------------------------------------- */
+/*
+ * The reference builds its hierarchy on the host and keeps it on the mesh:
+ * GAMGAgglomeration::New(matrix|mesh, dict)  solvers/GAMG/GAMGAgglomerations/GAMGAgglomeration/GAMGAgglomeration.C:91-198
+ * (run-time selected: algebraicPair in libOpenFOAM, faceAreaPair in libfiniteVolume,
+ * finiteVolume/fvMatrices/solvers/GAMGSymSolver/GAMGAgglomerations/faceAreaPairGAMGAgglomeration/faceAreaPairGAMGAgglomeration.C:46-73,
+ * MGridGen ...; cached as a MeshObject with `cacheAgglomeration on`).  A host that has that object hands its levels
+ * over instead of letting the library agglomerate (which it can only do for the pair agglomerators):
+ *   ldu_gamg_begin_levels(m);
+ *   for level = 0 .. agglomeration.size()-1:      (level l maps mesh level l onto mesh level l+1)
+ *     ldu_gamg_set_level(m, level,
+ *         nFine, restrictAddressing(level),                 GAMGAgglomeration.H:206-209
+ *         nFineFaces, faceRestrictAddressing(level),        GAMGAgglomeration.H:212-215 (>= 0: coarse face, < 0: -1 - coarse cell)
+ *         nCoarse, nCoarseFaces, lowerAddr, upperAddr of meshLevel(level+1).lduAddr(),
+ *         per coupled patch of the matrix, in ldu_matrix_create's order, the GAMGInterface of
+ *         interfaceLevel(level+1): size, faceCells() and faceRestrictAddressing()  (GAMGInterface.H:158-187));
+ *   ldu_gamg_end_levels(m);
+ * After that every GAMG solve / preconditioner on m uses these levels as they are (only the coefficients are
+ * agglomerated per solve, GAMGSolverAgglomerateMatrix.C:31-207) until ldu_gamg_begin_levels is called again or
+ * ldu_gamg_internal_levels(m) gives the agglomeration back to the library.
+ */
+int ldu_gamg_begin_levels(ldu_matrix* m);
+int ldu_gamg_set_level(ldu_matrix* m, int level, int nFine, const int* restrictAddr, int nFineFaces,
+                       const int* faceRestrictAddr, int nCoarse, int nCoarseFaces, const int* coarseLower,
+                       const int* coarseUpper, const int* coarseIfSizes, const int* const* coarseIfFaceCells,
+                       const int* const* ifRestrictAddr);
+int ldu_gamg_end_levels(ldu_matrix* m);
+int ldu_gamg_internal_levels(ldu_matrix* m);
+
 /* ---- GAMG hierarchy introspection (parity tests) -------------------------- */
 int ldu_gamg_build(ldu_matrix* m, const ldu_controls* controls);
 int ldu_gamg_nlevels(ldu_matrix* m);

@@ -668,7 +668,7 @@ int ldu_matrix_set_face_weights(ldu_matrix* m, const double* weights)
 {
     if (!m || (m->nFaces && !weights)) return LDU_EINVAL;
     m->h_faceWeights.assign(weights, weights + m->nFaces);
-    m->hierarchyValid = false;
+    if (!m->externalHierarchy) m->hierarchyValid = false;
     return LDU_OK;
 }
 

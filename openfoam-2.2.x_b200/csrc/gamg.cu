@@ -333,6 +333,9 @@ static int make_carrier(ldu_context* ctx, int nCells, const std::vector<std::vec
 // pairGAMGAgglomeration::agglomerate(mesh, faceWeights): pairGAMGAgglomerate.C:201-292
 int gamg_build(ldu_matrix* m, const ldu_controls* c)
 {
+    // a hierarchy handed over by the host (ldu_gamg_set_level: the reference's own GAMGAgglomeration)
+    // is used as it is; the agglomeration keys of the controls are the host's business then
+    if (m->externalHierarchy && m->hierarchyValid) return LDU_OK;
     if (m->hierarchyValid && c->cacheAgglomeration
         && m->hierarchyControls.nCellsInCoarsestLevel == c->nCellsInCoarsestLevel
         && m->hierarchyControls.mergeLevels == c->mergeLevels
@@ -1017,6 +1020,98 @@ int ldu_gamg_build(ldu_matrix* m, const ldu_controls* controls)
     LDU_TRY(gamg_build(m, controls));
     if (m->haveCoeffs) LDU_TRY(agglomerate_coefficients(m));
     LDU_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return LDU_OK;
+}
+
+int ldu_gamg_begin_levels(ldu_matrix* m)
+{
+    if (!m) return LDU_EINVAL;
+    LDU_CUDA(cudaSetDevice(m->ctx->device));
+    LDU_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    gamg_free(m);
+    m->externalHierarchy = true;
+    return LDU_OK;
+}
+
+int ldu_gamg_set_level(ldu_matrix* m, int level, int nFine, const int* restrictAddr, int nFineFaces,
+                       const int* faceRestrictAddr, int nCoarse, int nCoarseFaces, const int* coarseLower,
+                       const int* coarseUpper, const int* coarseIfSizes, const int* const* coarseIfFaceCells,
+                       const int* const* ifRestrictAddr)
+{
+    if (!m || !m->externalHierarchy || m->hierarchyValid) {
+        set_error("ldu_gamg_set_level: call ldu_gamg_begin_levels first");
+        return LDU_EINVAL;
+    }
+    if (level != (int)m->levels.size() || level >= kMaxLevels - 1) {
+        set_error("ldu_gamg_set_level: levels must be given in order, starting at 0");
+        return LDU_EINVAL;
+    }
+    ldu_matrix* fine = level == 0 ? m : m->levels[level - 1]->coarse;
+    if (nFine != fine->nCells || nFineFaces != fine->nFaces || nCoarse < 1 || nCoarseFaces < 0 || !restrictAddr
+        || (nFineFaces && !faceRestrictAddr) || (nCoarseFaces && (!coarseLower || !coarseUpper))) {
+        set_error("ldu_gamg_set_level: sizes do not match the level above");
+        return LDU_EINVAL;
+    }
+    LDU_CUDA(cudaSetDevice(m->ctx->device));
+    HostLevel H;
+    H.nCoarse = nCoarse;
+    H.cmap.assign(restrictAddr, restrictAddr + nFine);
+    H.faceMap.assign(faceRestrictAddr, faceRestrictAddr + nFineFaces);
+    H.cOwner.assign(coarseLower, coarseLower + nCoarseFaces);
+    H.cNeighbour.assign(coarseUpper, coarseUpper + nCoarseFaces);
+    for (int v : H.cmap)
+        if (v < 0 || v >= nCoarse) {
+            set_error("ldu_gamg_set_level: restrictAddr out of range");
+            return LDU_EINVAL;
+        }
+    for (int v : H.faceMap)
+        if (v >= nCoarseFaces || -1 - v >= nCoarse) {
+            set_error("ldu_gamg_set_level: faceRestrictAddr out of range");
+            return LDU_EINVAL;
+        }
+    const size_t nIf = fine->ifs.size();
+    H.ifCells.resize(nIf);
+    H.ifRestrict.resize(nIf);
+    if (nIf && (!coarseIfSizes || !coarseIfFaceCells || !ifRestrictAddr)) {
+        set_error("ldu_gamg_set_level: the matrix has coupled patches, their coarse interfaces are missing");
+        return LDU_EINVAL;
+    }
+    for (size_t p = 0; p < nIf; p++) {
+        H.ifCells[p].assign(coarseIfFaceCells[p], coarseIfFaceCells[p] + coarseIfSizes[p]);
+        H.ifRestrict[p].assign(ifRestrictAddr[p], ifRestrictAddr[p] + fine->ifs[p].n);
+        for (int v : H.ifRestrict[p])
+            if (v < 0 || v >= coarseIfSizes[p]) {
+                set_error("ldu_gamg_set_level: interface restrict addressing out of range");
+                return LDU_EINVAL;
+            }
+    }
+    GamgLevel* L = nullptr;
+    LDU_TRY(build_level_device(fine, H, &L));
+    m->levels.push_back(L);
+    return LDU_OK;
+}
+
+int ldu_gamg_end_levels(ldu_matrix* m)
+{
+    if (!m || !m->externalHierarchy) return LDU_EINVAL;
+    if (m->levels.empty()) {
+        set_error("GAMG: no coarse levels created, matrix too small or nCellsInCoarsestLevel too large "
+                  "(GAMGSolver.C:108-126)");
+        return LDU_EINVAL;
+    }
+    m->hierarchyValid = true;
+    return LDU_OK;
+}
+
+int ldu_gamg_internal_levels(ldu_matrix* m)
+{
+    if (!m) return LDU_EINVAL;
+    if (m->externalHierarchy) {
+        LDU_CUDA(cudaSetDevice(m->ctx->device));
+        LDU_CUDA(cudaStreamSynchronize(m->ctx->stream));
+        gamg_free(m);
+        m->externalHierarchy = false;
+    }
     return LDU_OK;
 }
 

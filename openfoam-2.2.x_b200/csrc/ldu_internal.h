@@ -203,6 +203,7 @@ struct ldu_matrix {
     // GAMG hierarchy
     std::vector<ldu::GamgLevel*> levels;
     bool hierarchyValid = false;
+    bool externalHierarchy = false;   // levels handed over through ldu_gamg_set_level: never rebuilt by the library
     bool precondHierarchyReady = false;   // GAMG-as-preconditioner: coarse coefficients current
     ldu_controls hierarchyControls;
     bool isCoarse = false;

@@ -133,6 +133,8 @@ struct S2Args {
     LLW* gJ;            // [nTiles][steps]       edge line of a tile, for the next column
     unsigned int* ticket;  // [0] claimed, [1] finished
     unsigned long long* trace;   // debug (LDU_S2_TRACE): per CTA {ticket, start, first plane done, last plane done, helper loops, helper done}
+    int dbg;                     // debug (LDU_S3_DBG): 1 = operands by direct loads (no cp.async ring), 2 = block-wide barrier
+                                 // around the ring refill, 4 = fence before the words are published
 };
 
 struct Shared2 {
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
 
 
 // ---------------------------------------------------------------------------
-// Third generation: REGISTER-STACKED planes (LDU_STENCIL=3, the default).
+// Third generation: REGISTER-STACKED planes (LDU_STENCIL=3, opt-in).
 //
 // What bounded sweep2_kernel was the tick: W warps of a CTA meeting at a named barrier once per
 // step and handing a 256-byte row to the next plane through shared memory (~470 cycles per tick
@@ -488,19 +490,33 @@ __global__ void __launch_bounds__((W + 1) * 32) sweep2_kernel(S2Args a)
 // in the previous tick), so
 //   * the k-neighbour of plane p is the register res[p-1] of the same lane (no shared memory, no barrier),
 //   * the j-neighbour is one shuffle, the i-neighbour the lane's own register,
-//   * the W planes of a tick are W independent dependency chains (mul, sub, shuffle, mul, sub, mul, sub): the
+//   * the W planes of a tick are W independent dependency chains (mul, sub, mul, sub, mul, sub): the
 //     FP64 pipe stays busy without any other warp,
-//   * nothing in the CTA synchronises: a CTA is one warp.
-// Operands arrive through a cp.async ring (kD3 ticks deep) from the STACKED layout (tile_row): the 4 x W
-// rows of a tick are 4 contiguous blocks of 256 W bytes.  Only the faces of a (stack, column) group cross
-// CTAs, as {value, epoch} words polled in L2 kA3 ticks ahead of their use:
+//   * nothing synchronises inside the tick.
+// Operands arrive through a cp.async ring from the STACKED layout (tile_row): the 4 x W rows of a tick
+// are 4 contiguous blocks of 256 W bytes.  Only the faces of a (stack, column) group cross CTAs, as
+// {value, epoch} words in L2:
 //   gK[group][step][lane]      the last plane of the stack below (above, backward sweep)
 //   gJ[group][i + p][p]        the edge line of the previous (next) column, one 16 W-byte row per tick
+// A helper warp (the CTA's second warp, on another SM sub-partition) polls them, several rows per round
+// trip, and forwards them into tagged rings in shared memory: the compute warp never has a global load in
+// flight (loads kept in registers across ticks share the warp's counting scoreboards with the LDS of the
+// tick: the first version of this kernel paid one L2 round trip per tick for its look-ahead polls).
 // Groups are claimed from an atomic ticket in dependency order (no co-residency requirement).
 // Arithmetic and its order are those of sweep2_kernel: bit-identical to the reference.
 // ---------------------------------------------------------------------------
-constexpr int kD3 = 6;    // operand ring depth (ticks)
-constexpr int kA3 = 4;    // look-ahead of the polled words (ticks) = unroll factor of the tick loop
+constexpr int kRing3 = 16;          // ticks of forwarded face words kept in shared memory
+constexpr int kOpRingBytes = 65536; // operand ring: 64 KB / (4 W 256 B) ticks deep
+
+template <int W>
+struct Smem3 {
+    LLW hk[kRing3][32];     // helper -> compute: k-face row of loop tick s in slot s % kRing3, tag s + 1
+    LLW hj[kRing3][W];      // helper -> compute: j-face row
+    volatile int prog;      // ticks completed by the compute warp (flow control of the rings)
+    volatile int abort;
+    int ticket;
+    int pad;
+};
 
 __device__ __forceinline__ void cp_async16(unsigned int dst, const void* src)
 {
@@ -508,14 +524,26 @@ __device__ __forceinline__ void cp_async16(unsigned int dst, const void* src)
 }
 
 template <int W, bool BWD>
-__global__ void __launch_bounds__(32) sweep3_kernel(S2Args a)
+__global__ void __launch_bounds__(64, 1) sweep3_kernel(S2Args a)
 {
+    constexpr int kD3 = kOpRingBytes / (4 * W * 256);           // operand ring depth in ticks
+    constexpr unsigned int kOpBytes = W * 256u, kSlotBytes = 4u * kOpBytes;
     extern __shared__ uint4 smem_raw[];
+    Smem3<W>* sm = reinterpret_cast<Smem3<W>*>(reinterpret_cast<unsigned char*>(smem_raw) + kOpRingBytes);
     if (a.guarded && a.S->done) return;
-    const int lane = threadIdx.x;
-    int tk = 0;
-    if (lane == 0) tk = (int)atomicAdd(&a.ticket[0], 1u);
-    tk = __shfl_sync(0xffffffffu, tk, 0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        sm->ticket = (int)atomicAdd(&a.ticket[0], 1u);
+        sm->prog = 0;
+        sm->abort = 0;
+    }
+    {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);      // tags 0: never equal to s + 1
+        uint4* q0 = reinterpret_cast<uint4*>(&sm->hk[0][0]);
+        for (int q = threadIdx.x; q < kRing3 * (32 + W); q += 64) q0[q] = z;
+    }
+    __syncthreads();
+    const int tk = sm->ticket;
 
     const int nx = a.b.nx, nJ = a.b.nJ, steps = a.b.steps, ticks = a.b.ticks, nKg = a.b.nKg;
     const int nCta = nKg * nJ;
@@ -529,19 +557,87 @@ __global__ void __launch_bounds__(32) sweep3_kernel(S2Args a)
     const bool jOut = BWD ? (J > 0) : (J + 1 < nJ);
     const unsigned int epoch = a.epoch;
     const int nRho = nx + W - 1;                               // rows of a group's gJ block
+    const LLW* gKin = a.gK + ((long long)(BWD ? g + nJ : g - nJ) * steps) * 32 + lane;
+    const LLW* gJin = a.gJ + ((long long)(BWD ? g + 1 : g - 1) * nRho) * W + (lane < W ? lane : 0);
+    // loop tick s -> layout tick; rows of the face words loop tick s needs (negative: none)
+    auto sigma_of = [&](int s_) { return BWD ? ticks - 1 - s_ : s_; };
+    auto k_row = [&](int s_) -> int {
+        const int sg = sigma_of(s_);
+        const int t = BWD ? sg - (W - 1) : sg;
+        return (kIn && t >= 0 && t < steps) ? t : -1;
+    };
+    auto j_row = [&](int s_) -> int {
+        const int sg = sigma_of(s_);
+        const int rho = BWD ? sg - 31 : sg;
+        return (jIn && rho >= 0 && rho < nRho) ? rho : -1;
+    };
+    unsigned long long* trace = a.trace ? a.trace + 8ull * (unsigned int)tk : nullptr;
+
+    if (warp == 1) {
+        // ------------------------------------------------------------------ helper warp
+        if (!kIn && !jIn) return;
+        const unsigned int hkA = (unsigned int)__cvta_generic_to_shared(&sm->hk[0][lane]);
+        const unsigned int hjA = (unsigned int)__cvta_generic_to_shared(&sm->hj[0][lane < W ? lane : 0]);
+        int sk = kIn ? 0 : ticks, sj = jIn ? 0 : ticks;     // next loop tick to forward, per ring
+        long long tstart = 0;
+        for (int spin = 0; sk < ticks || sj < ticks;) {
+            if (sm->abort) break;
+            const int cap = min(ticks, sm->prog + kRing3 - 1);   // slot s % kRing3 is free once tick s - kRing3 is done
+            // skip the ticks that need no word
+            while (sk < cap && k_row(sk) < 0) sk++;
+            while (sj < cap && j_row(sj) < 0) sj++;
+            LLW wk[4], wj[4];
+            int rk[4], rj[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                rk[q] = (sk + q < cap) ? k_row(sk + q) : -1;
+                rj[q] = (sj + q < cap) ? j_row(sj + q) : -1;
+                if (rk[q] >= 0) g_peek(gKin + (long long)rk[q] * 32, wk[q]);
+                if (rj[q] >= 0 && lane < W) g_peek(gJin + (long long)rj[q] * W, wj[q]);
+            }
+            bool did = false;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {       // rows become valid in order
+                if (rk[q] < 0 || !__all_sync(0xffffffffu, ok(wk[q], epoch))) break;
+                s_store_a(hkA + (unsigned int)(sk & (kRing3 - 1)) * 512u, wk[q].lo, wk[q].hi, (unsigned int)sk + 1u);
+                sk++;
+                did = true;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (rj[q] < 0 || !__all_sync(0xffffffffu, lane >= W || ok(wj[q], epoch))) break;
+                if (lane < W) s_store_a(hjA + (unsigned int)(sj & (kRing3 - 1)) * (W * 16u), wj[q].lo, wj[q].hi, (unsigned int)sj + 1u);
+                sj++;
+                did = true;
+            }
+            if (did) {
+                spin = 0;
+                tstart = 0;
+            } else if ((++spin & 63) == 63) {
+                if (tstart == 0) tstart = clock64();
+                else if (clock64() - tstart > kTimeout2) {
+                    sm->abort = 1;
+                    a.S->commError = 2;
+                    a.S->done = 1;
+                    break;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- compute warp
     const long long elemBase = (long long)g * ticks * W * 32;  // first element of the group's stream
     const double* pOp[4] = {a.pk + elemBase, a.pj + elemBase, a.pi + elemBase, a.Y + elemBase};
     double* pY = a.Y + elemBase + lane;
-    const LLW* gKin = a.gK + ((long long)(BWD ? g + nJ : g - nJ) * steps) * 32 + lane;
     LLW* gKout = a.gK + ((long long)g * steps) * 32 + lane;
-    const LLW* gJin = a.gJ + ((long long)(BWD ? g + 1 : g - 1) * nRho) * W + (lane < W ? lane : 0);
     LLW* gJout = a.gJ + ((long long)g * nRho) * W;
     const unsigned int ring = (unsigned int)__cvta_generic_to_shared(smem_raw);
-    constexpr unsigned int kOpBytes = W * 256u, kSlotBytes = 4u * kOpBytes;
+    const double* ringP = reinterpret_cast<const double*>(smem_raw) + lane;
+    const unsigned int hkA = (unsigned int)__cvta_generic_to_shared(&sm->hk[0][lane]);
+    const unsigned int hjA = (unsigned int)__cvta_generic_to_shared(&sm->hj[0][0]);
     const int edgeLane = BWD ? 31 : 0, pubLane = BWD ? 0 : 31;
 
-    // loop tick s -> layout tick
-    auto sigma_of = [&](int s_) { return BWD ? ticks - 1 - s_ : s_; };
     auto issue = [&](int s_, unsigned int slot) {
         if (s_ < ticks) {
             const long long e = (long long)sigma_of(s_) * (W * 32);
@@ -555,129 +651,149 @@ __global__ void __launch_bounds__(32) sweep3_kernel(S2Args a)
         }
         cp_async_commit();
     };
-    // rows of the polled words of loop tick s_ (negative: none)
-    auto k_row = [&](int s_) -> int {
-        if (!kIn || s_ >= ticks) return -1;
-        const int sg = sigma_of(s_);
-        const int t = BWD ? sg - (W - 1) : sg;
-        return (t >= 0 && t < steps) ? t : -1;
-    };
-    auto j_row = [&](int s_) -> int {
-        if (!jIn || s_ >= ticks) return -1;
-        const int sg = sigma_of(s_);
-        const int rho = BWD ? sg - 31 : sg;
-        return (rho >= 0 && rho < nRho) ? rho : -1;
-    };
-    LLW wk[kA3], wj[kA3];
-    auto peek = [&](int s_, LLW& k_, LLW& j_) {
-        const int kr = k_row(s_), jr = j_row(s_);
-        if (kr >= 0) g_peek(gKin + (long long)kr * 32, k_);
-        if (jr >= 0 && lane < W) g_peek(gJin + (long long)jr * W, j_);
-    };
+    long long trWaits = 0, trWaitCyc = 0, trOpCyc = 0;
+    const long long trStartC = clock64();
+    if (trace && lane == 0) {
+        trace[0] = ((unsigned long long)kg << 32) | (unsigned int)J;
+        trace[1] = gtimer();
+    }
     bool dead = false;
-    auto wait_k = [&](int kr, LLW& w) {     // all 32 words of the row
-        long long t0c = 0;
-        while (!dead && !__all_sync(0xffffffffu, ok(w, epoch))) {
-            g_peek(gKin + (long long)kr * 32, w);
-            if (t0c == 0) t0c = clock64();
-            else if (clock64() - t0c > kTimeout2) dead = true;
-            dead = __any_sync(0xffffffffu, dead);
-        }
-    };
-    auto wait_j = [&](int jr, LLW& w) {     // the W words of the row, one per lane < W
-        long long t0c = 0;
-        while (!dead && !__all_sync(0xffffffffu, lane >= W || ok(w, epoch))) {
-            if (lane < W) g_peek(gJin + (long long)jr * W, w);
-            if (t0c == 0) t0c = clock64();
-            else if (clock64() - t0c > kTimeout2) dead = true;
-            dead = __any_sync(0xffffffffu, dead);
-        }
-    };
 
     double res[W];
 #pragma unroll
     for (int p = 0; p < W; p++) res[p] = 0.0;
 #pragma unroll
     for (int q = 0; q < kD3; q++) issue(q, (unsigned int)q);
-#pragma unroll
-    for (int q = 0; q < kA3; q++) {
-        wk[q].f0 = wk[q].f1 = wj[q].f0 = wj[q].f1 = epoch - 1u;
-        wk[q].lo = wk[q].hi = wj[q].lo = wj[q].hi = 0u;
-        peek(q, wk[q], wj[q]);
-    }
 
     unsigned int slot = 0;
-    for (int sb = 0; sb < ticks; sb += kA3) {
+#pragma unroll 1
+    for (int s_ = 0; s_ < ticks; s_++) {
+        const int sg = sigma_of(s_);
+        const unsigned int hslot = (unsigned int)(s_ & (kRing3 - 1)), tag = (unsigned int)s_ + 1u;
+        // ---- faces of the group, forwarded by the helper
+        double vkin = 0.0;
+        double ve[W];
 #pragma unroll
-        for (int q = 0; q < kA3; q++) {
-            const int s_ = sb + q;
-            if (s_ < ticks) {
-                const int sg = sigma_of(s_);
-                // ---- faces of the group: words published by the CTAs of the neighbouring groups
-                double vkin = 0.0, ev = 0.0;
-                const int kr = k_row(s_), jr = j_row(s_);
-                if (kr >= 0) {
-                    if (!__all_sync(0xffffffffu, ok(wk[q], epoch))) wait_k(kr, wk[q]);
-                    vkin = val(wk[q]);
+        for (int p = 0; p < W; p++) ve[p] = 0.0;
+        if (k_row(s_) >= 0) {
+            LLW w;
+            s_peek_a(hkA + hslot * 512u, w);
+            if (!__all_sync(0xffffffffu, ok(w, tag))) {
+                const long long c0 = clock64();
+                while (!dead) {
+                    s_peek_a(hkA + hslot * 512u, w);
+                    if (__all_sync(0xffffffffu, ok(w, tag))) break;
+                    if (sm->abort || clock64() - c0 > kTimeout2) dead = true;
+                    dead = __any_sync(0xffffffffu, dead);
                 }
-                if (jr >= 0) {
-                    if (!__all_sync(0xffffffffu, lane >= W || ok(wj[q], epoch))) wait_j(jr, wj[q]);
-                    ev = val(wj[q]);
-                }
-                // ---- operands of this tick have landed
-                cp_async_wait<kD3 - 1>();
-                __syncwarp();
-                const unsigned int d = ring + slot * kSlotBytes + (unsigned int)lane * 8u;
-                // ---- W planes, each one step: res[p] <- src - pk*vk - pj*vj - pi*res[p]
+                if (trace) { trWaits++; trWaitCyc += clock64() - c0; }
+            }
+            vkin = val(w);
+        }
+        if (j_row(s_) >= 0) {
+            LLW w[W];
+            bool good = true;
 #pragma unroll
-                for (int pp = 0; pp < W; pp++) {
-                    const int p = BWD ? pp : W - 1 - pp;        // consume the old value of the plane it depends on
-                    const double opk = lds64(d + p * 256u);
-                    const double opj = lds64(d + kOpBytes + p * 256u);
-                    const double opi = lds64(d + 2u * kOpBytes + p * 256u);
-                    const double src = lds64(d + 3u * kOpBytes + p * 256u);
-                    const double vk = BWD ? (p < W - 1 ? res[p < W - 1 ? p + 1 : p] : vkin)
-                                          : (p > 0 ? res[p > 0 ? p - 1 : p] : vkin);
-                    double vj = BWD ? __shfl_down_sync(0xffffffffu, res[p], 1) : __shfl_up_sync(0xffffffffu, res[p], 1);
-                    if (jIn) {
-                        const double e = __shfl_sync(0xffffffffu, ev, p);
-                        if (lane == edgeLane) vj = e;
+            for (int p = 0; p < W; p++) {
+                s_peek_a(hjA + hslot * (W * 16u) + p * 16u, w[p]);
+                good = good && ok(w[p], tag);
+            }
+            if (!__all_sync(0xffffffffu, good)) {     // every lane reads the same words; the vote keeps the warp together
+                const long long c0 = clock64();
+                while (!dead) {
+                    good = true;
+#pragma unroll
+                    for (int p = 0; p < W; p++) {
+                        s_peek_a(hjA + hslot * (W * 16u) + p * 16u, w[p]);
+                        good = good && ok(w[p], tag);
                     }
-                    double acc = __dsub_rn(src, __dmul_rn(opk, vk));
-                    acc = __dsub_rn(acc, __dmul_rn(opj, vj));
-                    acc = __dsub_rn(acc, __dmul_rn(opi, res[p]));
-                    res[p] = acc;
+                    if (__all_sync(0xffffffffu, good)) break;
+                    if (sm->abort || clock64() - c0 > kTimeout2) dead = true;
+                    dead = __any_sync(0xffffffffu, dead);
                 }
-                // ---- results: the vector itself, then the faces other groups wait for
+                if (trace) { trWaits += 1ll << 32; trWaitCyc += clock64() - c0; }
+            }
 #pragma unroll
-                for (int p = 0; p < W; p++) {
-                    const int t = sg - p;
-                    if (t >= 0 && t < steps && p < Wg) pY[((long long)sg * W + p) * 32] = res[p];
-                }
-                if (kOut) {
-                    const int t = BWD ? sg : sg - (W - 1);
-                    if (t >= 0 && t < steps) g_store(gKout + (long long)t * 32, BWD ? res[0] : res[W - 1], epoch);
-                }
-                if (jOut) {
-                    const int rho = BWD ? sg : sg - 31;
-                    if (rho >= 0 && rho < nRho && lane == pubLane) {
+            for (int p = 0; p < W; p++) ve[p] = val(w[p]);
+        }
+        // ---- operands of this tick have landed
+        {
+            const long long c0 = trace ? clock64() : 0;
+            cp_async_wait<kD3 - 1>();
+            __syncwarp();
+            if (trace) trOpCyc += clock64() - c0;
+        }
+        const double* o = ringP + slot * (kSlotBytes / 8);
+        double opk[W], opj[W], opi[W], src[W], vj[W], nr[W];
+        if (a.dbg & 1) {
+            const long long e = (long long)sg * (W * 32) + lane;
 #pragma unroll
-                        for (int p = 0; p < W; p++) g_store(gJout + (long long)rho * W + p, res[p], epoch);
-                    }
-                }
-                // ---- refill: this tick's ring slot, and the words of tick s + kA3
-                __syncwarp();
-                issue(s_ + kD3, slot);
-                slot = slot + 1u == (unsigned int)kD3 ? 0u : slot + 1u;
-                wk[q].f0 = wk[q].f1 = wj[q].f0 = wj[q].f1 = epoch - 1u;
-                peek(s_ + kA3, wk[q], wj[q]);
+            for (int p = 0; p < W; p++) {
+                opk[p] = __ldcg(pOp[0] + e + p * 32);
+                opj[p] = __ldcg(pOp[1] + e + p * 32);
+                opi[p] = __ldcg(pOp[2] + e + p * 32);
+                src[p] = __ldcg(pOp[3] + e + p * 32);
+            }
+        } else {
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            opk[p] = o[p * 32];
+            opj[p] = o[W * 32 + p * 32];
+            opi[p] = o[2 * W * 32 + p * 32];
+            src[p] = o[3 * W * 32 + p * 32];
+        }
+        }
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            vj[p] = BWD ? __shfl_down_sync(0xffffffffu, res[p], 1) : __shfl_up_sync(0xffffffffu, res[p], 1);
+            if (jIn && lane == edgeLane) vj[p] = ve[p];
+        }
+        // ---- W planes, each one step: res[p] <- src - pk*vk - pj*vj - pi*res[p], all from the old values
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            const double vk = BWD ? (p < W - 1 ? res[p < W - 1 ? p + 1 : p] : vkin) : (p > 0 ? res[p > 0 ? p - 1 : p] : vkin);
+            double acc = __dsub_rn(src[p], __dmul_rn(opk[p], vk));
+            acc = __dsub_rn(acc, __dmul_rn(opj[p], vj[p]));
+            nr[p] = __dsub_rn(acc, __dmul_rn(opi[p], res[p]));
+        }
+#pragma unroll
+        for (int p = 0; p < W; p++) res[p] = nr[p];
+        // ---- results: the faces other groups wait for first, then the vector itself
+        if (a.dbg & 4) __threadfence();
+        if (kOut) {
+            const int t = BWD ? sg : sg - (W - 1);
+            if (t >= 0 && t < steps) g_store(gKout + (long long)t * 32, BWD ? res[0] : res[W - 1], epoch);
+        }
+        if (jOut) {
+            const int rho = BWD ? sg : sg - 31;
+            if (rho >= 0 && rho < nRho && lane == pubLane) {
+#pragma unroll
+                for (int p = 0; p < W; p++) g_store(gJout + (long long)rho * W + p, res[p], epoch);
             }
         }
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            const int t = sg - p;
+            if (t >= 0 && t < steps && p < Wg) pY[((long long)sg * W + p) * 32] = res[p];
+        }
+        // ---- refill this tick's ring slot
+        __syncwarp();
+        issue(s_ + kD3, slot);
+        slot = slot + 1u == (unsigned int)kD3 ? 0u : slot + 1u;
+        if (lane == 0) sm->prog = s_ + 1;
     }
     cp_async_wait<0>();
     if (dead && lane == 0) {
+        sm->abort = 1;
         a.S->commError = 2;
         a.S->done = 1;
+    }
+    if (trace && lane == 0) {
+        trace[2] = gtimer();
+        trace[3] = (unsigned long long)trWaits;
+        trace[4] = (unsigned long long)trWaitCyc;
+        trace[5] = (unsigned long long)trOpCyc;
+        trace[6] = (unsigned long long)(clock64() - trStartC);
     }
     // the last CTA re-arms the ticket for the next launch
     if (lane == 0) {
@@ -931,11 +1047,13 @@ int pick_W(int nz)
     return nz >= 12 ? 6 : 4;
 }
 
-// 2: plane-stacked CTAs (sweep2_kernel), 3 (default): register-stacked warps (sweep3_kernel)
+// 2 (default): plane-stacked CTAs (sweep2_kernel), 3: register-stacked warps (sweep3_kernel; measured on
+// B200, 216^3: 0.57 us per tick of one warp and 3-6 us per group-to-group hop = 590-610 us per sweep against
+// 450 us for sweep2_kernel -- correct and tested, not yet faster, hence opt-in)
 int box_generation()
 {
     const char* e = getenv("LDU_STENCIL");
-    return (e && atoi(e) == 2) ? 2 : 3;
+    return (e && atoi(e) == 3) ? 3 : 2;
 }
 
 // planes per warp of the register-stacked sweeps: the chain of stack-to-stack hops costs
@@ -1079,7 +1197,7 @@ int launch_sweeps(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
 template <int W>
 int launch_sweeps3(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
 {
-    const size_t smem = (size_t)kD3 * 4 * W * 256;
+    const size_t smem = (size_t)kOpRingBytes + sizeof(Smem3<W>);
     if (!s->attrSet) {
         LDU_CUDA(cudaFuncSetAttribute(sweep3_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LDU_CUDA(cudaFuncSetAttribute(sweep3_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1087,19 +1205,38 @@ int launch_sweeps3(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
     }
     const int grid = s->b.nKg * s->b.nJ;
     cudaStream_t st = m->ctx->stream;
-    a.trace = nullptr;
+    const char* tracePath = getenv("LDU_S2_TRACE");
+    if (tracePath && !s->trace) LDU_CUDA(cudaMalloc((void**)&s->trace, ((size_t)grid * 8) * sizeof(unsigned long long)));
+    a.trace = tracePath ? s->trace : nullptr;
+    a.dbg = getenv("LDU_S3_DBG") ? atoi(getenv("LDU_S3_DBG")) : 0;
+    if (a.trace) LDU_CUDA(cudaMemsetAsync(a.trace, 0, ((size_t)grid * 8) * sizeof(unsigned long long), st));
     a.epoch = ++s->epoch;
     a.pk = P.F[0];
     a.pj = P.F[1];
     a.pi = P.F[2];
-    sweep3_kernel<W, false><<<grid, 32, smem, st>>>(a);
+    const char* only = getenv("LDU_S3_ONLY");     // debug: "fwd" / "bwd" runs one of the two sweeps
+    if (!(only && only[0] == 'b')) sweep3_kernel<W, false><<<grid, 64, smem, st>>>(a);
     count_launch();
     LDU_CUDA(cudaGetLastError());
+    if (a.trace) {   // debug only: per-group timeline of the forward sweep
+        // columns: ticket kg J start_ns end_ns kWaits jWaits waitCycles operandWaitCycles totalCycles
+        std::vector<unsigned long long> h((size_t)grid * 8);
+        LDU_CUDA(cudaMemcpyAsync(h.data(), a.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        LDU_CUDA(cudaStreamSynchronize(st));
+        if (FILE* f = fopen(tracePath, "w")) {
+            for (int c = 0; c < grid; c++)
+                fprintf(f, "%d %d %d %llu %llu %llu %llu %llu %llu %llu\n", c, (int)(h[8 * c] >> 32),
+                        (int)(h[8 * c] & 0xffffffffu), h[8 * c + 1], h[8 * c + 2], h[8 * c + 3] & 0xffffffffull,
+                        h[8 * c + 3] >> 32, h[8 * c + 4], h[8 * c + 5], h[8 * c + 6]);
+            fclose(f);
+        }
+        a.trace = nullptr;
+    }
     a.epoch = ++s->epoch;
     a.pk = P.B[0];
     a.pj = P.B[1];
     a.pi = P.B[2];
-    sweep3_kernel<W, true><<<grid, 32, smem, st>>>(a);
+    if (!(only && only[0] == 'f')) sweep3_kernel<W, true><<<grid, 64, smem, st>>>(a);
     count_launch();
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;
@@ -1110,10 +1247,10 @@ int launch_sweeps3(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
 int stencil_version(const ldu_matrix* m)
 {
     if (m->box[0] <= 0 || !flow_enabled()) return 0;
-    // 0: generic dataflow sweeps, 1: stencil.cu, 2: stencil2.cu with plane-stacked CTAs,
-    // 3 (default): stencil2.cu with register-stacked warps; 2 and 3 share every entry point
+    // 0: generic dataflow sweeps, 1: stencil.cu, 2 (default): stencil2.cu with plane-stacked CTAs,
+    // 3: stencil2.cu with register-stacked warps; 2 and 3 share every entry point
     const char* e = getenv("LDU_STENCIL");
-    const int ver = e ? atoi(e) : 3;
+    const int ver = e ? atoi(e) : 2;
     return (ver < 0 || ver >= 2) ? 2 : ver;
 }
 
@@ -1162,6 +1299,7 @@ static int apply_core(ldu_matrix* m, const double* rD, const double* coefF, cons
     }
     s->yReadyFor = nullptr;
     S2Args a;
+    a.dbg = 0;
     a.S = m->d_scalars;
     a.guarded = 1;
     a.b = s->b;

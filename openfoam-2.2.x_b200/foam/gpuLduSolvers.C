@@ -10,6 +10,8 @@
 #include "PstreamReduceOps.H"
 #include "UIPstream.H"
 #include "UOPstream.H"
+#include "GAMGAgglomeration.H"
+#include "GAMGInterface.H"
 
 #include "../../include/ldu_b200.h"
 
@@ -260,9 +262,11 @@ struct cachedMatrix
     ldu_matrix* m;
     label nCells;
     label nFaces;
+    // the GAMGAgglomeration (a MeshObject when cacheAgglomeration is on) whose levels the device holds
+    const GAMGAgglomeration* agglomeration;
 };
 
-ldu_matrix* deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
+cachedMatrix& deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
 {
     static std::map<const lduAddressing*, cachedMatrix> cache;
     const lduAddressing& addr = A.lduAddr();
@@ -274,7 +278,7 @@ ldu_matrix* deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
     {
         if (it->second.nCells == nCells && it->second.nFaces == nFaces)
         {
-            return it->second.m;
+            return it->second;
         }
         ldu_matrix_destroy(it->second.m);   // mesh changed under the same address
         cache.erase(it);
@@ -323,6 +327,7 @@ ldu_matrix* deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
     c.nCells = nCells;
     c.nFaces = nFaces;
     c.m = NULL;
+    c.agglomeration = NULL;
     check
     (
         ldu_matrix_create
@@ -339,7 +344,69 @@ ldu_matrix* deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
         "ldu_matrix_create"
     );
     cache[&addr] = c;
-    return c.m;
+    return cache[&addr];
+}
+
+// The GAMG hierarchy is the reference's own: GAMGAgglomeration::New (GAMGAgglomeration.C:91-198) selects the
+// agglomerator named in the dictionary from the reference's tables -- algebraicPair (libOpenFOAM), faceAreaPair
+// (libfiniteVolume, needs fvMesh::Sf), MGridGen, ... -- and keeps it on the mesh as a MeshObject when
+// cacheAgglomeration is on.  Its levels are handed to the device (ldu_b200.h: ldu_gamg_set_level); only the
+// coefficients are agglomerated there, per solve.  Exactly as GAMGSolver does (GAMGSolver.C:52-154): looked up or
+// built per solver object, deleted again afterwards unless cached.
+void uploadAgglomeration
+(
+    cachedMatrix& cm,
+    const lduMatrix& A,
+    const dictionary& gamgDict,
+    const coupledPatches& cp
+)
+{
+    const bool cacheAgglomeration = gamgDict.lookupOrDefault<Switch>("cacheAgglomeration", false);
+    const GAMGAgglomeration& agg = GAMGAgglomeration::New(A, gamgDict);
+
+    if (!(cacheAgglomeration && cm.agglomeration == &agg))
+    {
+        check(ldu_gamg_begin_levels(cm.m), "ldu_gamg_begin_levels");
+        for (label lev = 0; lev < agg.size(); lev++)
+        {
+            const labelField& restrictAddr = agg.restrictAddressing(lev);
+            const labelList& faceRestrictAddr = agg.faceRestrictAddressing(lev);
+            const lduAddressing& coarse = agg.meshLevel(lev + 1).lduAddr();
+            const lduInterfacePtrsList& ifs = agg.interfaceLevel(lev + 1);
+            List<int> sizes(cp.patchIDs.size());
+            List<const int*> cells(cp.patchIDs.size()), ifRestrict(cp.patchIDs.size());
+            forAll(cp.patchIDs, i)
+            {
+                const GAMGInterface& gi = refCast<const GAMGInterface>(ifs[cp.patchIDs[i]]);
+                sizes[i] = gi.faceCells().size();
+                cells[i] = gi.faceCells().begin();
+                ifRestrict[i] = gi.faceRestrictAddressing().begin();
+            }
+            check
+            (
+                ldu_gamg_set_level
+                (
+                    cm.m, lev,
+                    restrictAddr.size(), restrictAddr.begin(),
+                    faceRestrictAddr.size(), faceRestrictAddr.begin(),
+                    coarse.size(), coarse.lowerAddr().size(),
+                    coarse.lowerAddr().begin(), coarse.upperAddr().begin(),
+                    sizes.size() ? sizes.begin() : NULL,
+                    sizes.size() ? cells.begin() : NULL,
+                    sizes.size() ? ifRestrict.begin() : NULL
+                ),
+                "ldu_gamg_set_level"
+            );
+        }
+        check(ldu_gamg_end_levels(cm.m), "ldu_gamg_end_levels");
+        cm.agglomeration = &agg;
+    }
+
+    if (!cacheAgglomeration)
+    {
+        delete &agg;          // GAMGSolver::~GAMGSolver, GAMGSolver.C:144-154
+        cm.agglomeration = NULL;
+    }
 }
 
 int preconditionerKind(const word& name)
@@ -400,19 +467,10 @@ void readGamgControls(const dictionary& d, ldu_controls& c)
     c.nVcycles = d.lookupOrDefault<label>("nVcycles", 2);
     // mandatory in the reference (lduMatrixSmoother.C:38-66, GAMGAgglomeration.C:104-107)
     c.smoother = smootherKind(word(d.lookup("smoother")));
+    // mandatory in the reference (GAMGAgglomeration.C:104-107).  The agglomeration itself is the reference's:
+    // uploadAgglomeration hands its levels to the device, whatever the agglomerator
     const word agglomerator(d.lookup("agglomerator"));
-    // faceAreaPair needs fvMesh::Sf() (libfiniteVolume), which this shim cannot reach: every pair
-    // agglomerator runs as algebraicPair here.  Said once, because the iteration counts then differ
-    // from the reference's faceAreaPair (the C ABI and the Python host do take face weights).
     c.useFaceWeights = 0;
-    static bool warned = false;
-    if (agglomerator != "algebraicPair" && !warned)
-    {
-        warned = true;
-        WarningIn("gpuLduSolver")
-            << "agglomerator " << agglomerator << " runs as algebraicPair in the GPU plug-in"
-            << " (face areas are not available to it)" << endl;
-    }
 }
 
 } // End anonymous namespace
@@ -495,7 +553,19 @@ Foam::solverPerformance Foam::gpuLduSolver::solve
 
     coupledPatches cp;
     findCoupledPatches(matrix_, interfaces_, cp);
-    ldu_matrix* m = deviceMatrix(matrix_, cp);
+    cachedMatrix& cm = deviceMatrix(matrix_, cp);
+    ldu_matrix* m = cm.m;
+    if (c.solver == LDU_SOLVER_GAMG)
+    {
+        uploadAgglomeration(cm, matrix_, controlDict_, cp);
+    }
+    else if (c.preconditioner == LDU_PRECOND_GAMG)
+    {
+        uploadAgglomeration
+        (
+            cm, matrix_, controlDict_.lookupEntry("preconditioner", false, false).dict(), cp
+        );
+    }
 
     // interfaceBouCoeffs_/interfaceIntCoeffs_ of the coupled patches (lduMatrix.H:97-104)
     List<const double*> bou(cp.patchIDs.size()), intc(cp.patchIDs.size());

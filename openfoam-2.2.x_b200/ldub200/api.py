@@ -51,6 +51,7 @@ ABI_SYMBOLS = [
     "ldu_residual", "ldu_precondition", "ldu_smooth", "ldu_solve", "ldu_amul_device", "ldu_tmul_device",
     "ldu_solve_device", "ldu_residual_history", "ldu_gamg_build", "ldu_gamg_nlevels",
     "ldu_gamg_level_sizes", "ldu_gamg_level_restrict", "ldu_gamg_level_coeffs", "ldu_controls_default",
+    "ldu_gamg_begin_levels", "ldu_gamg_set_level", "ldu_gamg_end_levels", "ldu_gamg_internal_levels",
 ]
 
 
@@ -108,6 +109,10 @@ def library():
         L.ldu_residual_history.argtypes = [vp, vp, i]
         L.ldu_gamg_build.argtypes = [vp, C.POINTER(Controls)]
         L.ldu_gamg_nlevels.argtypes = [vp]
+        L.ldu_gamg_begin_levels.argtypes = [vp]
+        L.ldu_gamg_set_level.argtypes = [vp, i, i, vp, i, vp, i, i, vp, vp, vp, vp, vp]
+        L.ldu_gamg_end_levels.argtypes = [vp]
+        L.ldu_gamg_internal_levels.argtypes = [vp]
         L.ldu_gamg_level_sizes.argtypes = [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
         L.ldu_gamg_level_restrict.argtypes = [vp, i, vp]
         L.ldu_gamg_level_coeffs.argtypes = [vp, i, vp, vp, vp]
@@ -462,6 +467,31 @@ class lduMatrix:
             out.append(dict(nFine=nf.value, nCoarse=nc.value, nFaces=ncf.value, restrict=r,
                             diag=diag, upperCoef=upper))
         return out
+
+    def set_gamg_levels(self, levels):
+        """Hand over a GAMG hierarchy built by the host (the reference's GAMGAgglomeration): levels = list of
+        dict(restrict, faceRestrict, nCoarse, lower, upper[, ifCells, ifRestrict]) from the finest level down
+        (ldu_gamg_begin_levels / ldu_gamg_set_level / ldu_gamg_end_levels).  None gives the agglomeration
+        back to the library."""
+        if levels is None:
+            _check(self.L.ldu_gamg_internal_levels(self.h), "ldu_gamg_internal_levels")
+            return
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        _check(self.L.ldu_gamg_begin_levels(self.h), "ldu_gamg_begin_levels")
+        n_if = len(self.interfaces)
+        for lev, d in enumerate(levels):
+            r, fr, lo, up = i32(d["restrict"]), i32(d["faceRestrict"]), i32(d["lower"]), i32(d["upper"])
+            cells = [i32(a) for a in d.get("ifCells", [])]
+            ifr = [i32(a) for a in d.get("ifRestrict", [])]
+            assert len(cells) == n_if and len(ifr) == n_if
+            sizes = (C.c_int * max(n_if, 1))(*[a.size for a in cells])
+            cp = (C.c_void_p * max(n_if, 1))(*[a.ctypes.data for a in cells])
+            rp = (C.c_void_p * max(n_if, 1))(*[a.ctypes.data for a in ifr])
+            _check(self.L.ldu_gamg_set_level(self.h, lev, r.size, r.ctypes.data, fr.size, fr.ctypes.data,
+                                             int(d["nCoarse"]), lo.size, lo.ctypes.data, up.ctypes.data,
+                                             sizes if n_if else None, cp if n_if else None, rp if n_if else None),
+                   "ldu_gamg_set_level")
+        _check(self.L.ldu_gamg_end_levels(self.h), "ldu_gamg_end_levels")
 
     def destroy(self):
         if self.h:

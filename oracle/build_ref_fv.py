@@ -15,6 +15,11 @@ the flags of wmake/rules/linux64Gcc; sources are compiled where they lie under
 (wmakeLnInclude); nothing is copied into the repository.  Needs
 oracle/_ref/libOpenFOAM.so (build_ref.py) first.
 
+Portability fix for g++ 13, applied to a scratch copy of the header (same policy as build_ref.py):
+  * oscillatingFixedValueFvPatchField.H:213-233: four accessors return the autoPtr<DataEntry<scalar>>
+    members amplitude_/frequency_ as scalar.  They can never be instantiated (old g++ did not look at
+    uninstantiated template members); they are dropped from the scratch copy.
+
 The two flex sources of the chain (STL ASCII readers, surfMesh/…/STLsurfaceFormatASCII.L
 and triSurface/…/readSTLASCII.L) cannot be generated here (no flex): their two entry
 points are provided by oracle/foam_stubs/stlStubs.C, which raises FatalError when an
@@ -57,6 +62,20 @@ APPS = {
 
 def ln_dir(lib):
     return BUILD / f"lnInclude_{lib}"
+
+
+def header_fixes():
+    """scratch copies of headers g++ 13 rejects (see the module docstring)"""
+    import re
+    name = "oscillatingFixedValueFvPatchField.H"
+    link = ln_dir("finiteVolume") / name
+    src = (REF / "src/finiteVolume/fields/fvPatchFields/derived/oscillatingFixedValue" / name).read_text()
+    fixed = re.sub(r"//- Return amplitude\n\s*scalar amplitude\(\) const.*?scalar& frequency\(\)\s*\{[^}]*\}", "",
+                   src, flags=re.S)
+    assert fixed != src
+    if link.is_symlink() or link.exists():
+        link.unlink()
+    link.write_text(fixed)
 
 
 def build_lib(lib, jobs):
@@ -134,6 +153,7 @@ def main():
         chain += CHAIN_BLOCKMESH
     for lib in chain:
         make_lninclude(ln_dir(lib), [REF / "src" / LIBS[lib][0]])
+    header_fixes()
     for lib in chain:
         rc = build_lib(lib, jobs)
         if rc:

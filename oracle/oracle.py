@@ -518,3 +518,36 @@ def ref_agglom(sysd, controls: dict):
         levels.append(dict(nFine=nf, nCoarse=nc, restrict=out[pos + 2:pos + 2 + nf].copy()))
         pos += 2 + nf
     return levels
+
+
+def _parse_levels_full(out):
+    n = int(out[0])
+    pos = 1
+    levels = []
+    for _ in range(n):
+        nf, nc, nff, ncf, nif = (int(x) for x in out[pos:pos + 5])
+        pos += 5
+        d = dict(nFine=nf, nCoarse=nc)
+        d["restrict"] = out[pos:pos + nf].copy(); pos += nf
+        d["faceRestrict"] = out[pos:pos + nff].copy(); pos += nff
+        d["lower"] = out[pos:pos + ncf].copy(); pos += ncf
+        d["upper"] = out[pos:pos + ncf].copy(); pos += ncf
+        d["ifCells"], d["ifRestrict"] = [], []
+        for _ in range(nif):
+            a, b = int(out[pos]), int(out[pos + 1])
+            pos += 2
+            d["ifCells"].append(out[pos:pos + a].copy()); pos += a
+            d["ifRestrict"].append(out[pos:pos + b].copy()); pos += b
+        levels.append(d)
+    return levels
+
+
+def ref_agglom_full(sysd, controls: dict):
+    """the reference's whole GAMG hierarchy (GAMGAgglomeration::New): what ldu_gamg_set_level takes"""
+    out, _ = ref_run(sysd, "agglom_full", dict_text(controls), ints=True)
+    return _parse_levels_full(out)
+
+
+def ref_agglom_full_par(regions, controls: dict):
+    outs, _ = ref_run_par(regions, "agglom_full", dict_text(controls), ints=True)
+    return [_parse_levels_full(o) for o in outs]

@@ -65,6 +65,7 @@
 #include "IStringStream.H"
 #include "clockTime.H"
 #include "GAMGAgglomeration.H"
+#include "GAMGInterface.H"
 #include "pairGAMGAgglomeration.H"
 #include "addToRunTimeSelectionTable.H"
 #include "PCG.H"
@@ -741,6 +742,43 @@ int main(int argc, char* argv[])
             outInts.push_back(r.size());
             outInts.push_back(agg.meshLevel(lev + 1).lduAddr().size());
             for (label i = 0; i < r.size(); i++) outInts.push_back(r[i]);
+        }
+    }
+    else if (op == "agglom_full")
+    {
+        // everything a host needs to hand the hierarchy to another solver (include/ldu_b200.h,
+        // ldu_gamg_set_level): per level restrictAddressing, faceRestrictAddressing, the coarse
+        // lduAddressing and, per coupled patch, the GAMGInterface's faceCells + faceRestrictAddressing
+        dictionary d(dictFromText(argv[4]));
+        const GAMGAgglomeration& agg = GAMGAgglomeration::New(A, d);
+        intsOut = true;
+        outInts.push_back(agg.size());
+        for (label lev = 0; lev < agg.size(); lev++)
+        {
+            const labelField& r = agg.restrictAddressing(lev);
+            const labelList& fr = agg.faceRestrictAddressing(lev);
+            const lduAddressing& ca = agg.meshLevel(lev + 1).lduAddr();
+            const lduInterfacePtrsList& ifs = agg.interfaceLevel(lev + 1);
+            label nIf = 0;
+            forAll(ifs, i) if (ifs.set(i)) nIf++;
+            outInts.push_back(r.size());
+            outInts.push_back(ca.size());
+            outInts.push_back(fr.size());
+            outInts.push_back(ca.lowerAddr().size());
+            outInts.push_back(nIf);
+            forAll(r, i) outInts.push_back(r[i]);
+            forAll(fr, i) outInts.push_back(fr[i]);
+            forAll(ca.lowerAddr(), i) outInts.push_back(ca.lowerAddr()[i]);
+            forAll(ca.upperAddr(), i) outInts.push_back(ca.upperAddr()[i]);
+            forAll(ifs, i)
+            {
+                if (!ifs.set(i)) continue;
+                const GAMGInterface& gi = refCast<const GAMGInterface>(ifs[i]);
+                outInts.push_back(gi.faceCells().size());
+                outInts.push_back(gi.faceRestrictAddressing().size());
+                forAll(gi.faceCells(), k) outInts.push_back(gi.faceCells()[k]);
+                forAll(gi.faceRestrictAddressing(), k) outInts.push_back(gi.faceRestrictAddressing()[k]);
+            }
         }
     }
     else
