@@ -161,6 +161,10 @@ def main():
     rc = build_app("icoFoam")
     if rc == 0 and "--blockMesh" in sys.argv:
         rc = build_app("blockMesh")
+        # blockMesh needs the real cell-model table (hex, prism, ...): a data file of the reference's etc/,
+        # placed beside the built binaries (oracle/_ref is build output, not repository content)
+        import shutil
+        shutil.copyfile(REF / "etc" / "cellModels", OUT / "etc" / "cellModels")
     return rc
 
 
