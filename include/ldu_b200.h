@@ -170,9 +170,14 @@ int ldu_matrix_destroy(ldu_matrix* m);
 int ldu_matrix_set_coeffs(ldu_matrix* m, const double* diag, const double* upper,
                           const double* lower, const double* const* bouCoeffs,
                           const double* const* intCoeffs);
-/* same, from device-resident arrays (no PCIe traffic) */
+/* same, from device-resident arrays (no PCIe traffic).  A matrix with coupled patches needs their
+ * boundary coefficients too: give them (host pointers, one array per interface, a few KB) with
+ * ldu_matrix_set_interface_coeffs before the first ldu_matrix_set_coeffs_device, and again whenever
+ * they change; without them the call fails with LDU_EINVAL. */
 int ldu_matrix_set_coeffs_device(ldu_matrix* m, const double* d_diag, const double* d_upper,
                                  const double* d_lower);
+int ldu_matrix_set_interface_coeffs(ldu_matrix* m, const double* const* bouCoeffs,
+                                    const double* const* intCoeffs);
 /* faceAreaPair agglomeration weights (finiteVolume/.../faceAreaPairGAMGAgglomeration.C:48-73) */
 int ldu_matrix_set_face_weights(ldu_matrix* m, const double* weights);
 

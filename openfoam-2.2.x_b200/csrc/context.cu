@@ -1,6 +1,7 @@
 // C-ABI entry points: library state, context, device memory, matrix objects.
 #include <algorithm>
 #include <cstring>
+#include <thread>
 
 #include "ldu_internal.h"
 #include "sweeps.h"
@@ -33,6 +34,138 @@ static int upload(ldu_context* ctx, T** d, const T* h, size_t n, size_t pad = 0)
     if (pad) LDU_CUDA(cudaMemsetAsync(*d + n, 0, pad * sizeof(T), ctx->stream));
     if (n) LDU_CUDA(cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     return LDU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// large copies from / to pageable host memory: several host threads stage chunks through pinned buffers
+// ---------------------------------------------------------------------------
+namespace {
+constexpr int kStageThreads = 6;
+constexpr size_t kStageChunk = 4u << 20;
+constexpr size_t kStageMin = 1u << 20;     // below this a plain copy is as fast
+
+struct StageWorker {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    unsigned char* buf[2] = {nullptr, nullptr};
+};
+struct StagePool {
+    StageWorker w[kStageThreads];
+};
+
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int stage_pool(ldu_context* ctx, StagePool** out)
+{
+    if (!ctx->stage) {
+        StagePool* sp = new StagePool();
+        ctx->stage = sp;
+        for (int t = 0; t < kStageThreads; t++) {
+            LDU_CUDA(cudaStreamCreateWithFlags(&sp->w[t].stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; b++) {
+                LDU_CUDA(cudaEventCreateWithFlags(&sp->w[t].ev[b], cudaEventDisableTiming));
+                LDU_CUDA(cudaMallocHost((void**)&sp->w[t].buf[b], kStageChunk));
+            }
+        }
+    }
+    *out = reinterpret_cast<StagePool*>(ctx->stage);
+    return LDU_OK;
+}
+
+// chunk k of the copy belongs to worker k % kStageThreads, buffer (k / kStageThreads) % 2
+int staged_copy(ldu_context* ctx, unsigned char* dst, const unsigned char* src, size_t bytes, bool toDevice)
+{
+    StagePool* sp = nullptr;
+    LDU_TRY(stage_pool(ctx, &sp));
+    LDU_CUDA(cudaStreamSynchronize(ctx->stream));     // ordered after what is queued on the context's stream
+    const size_t nChunks = (bytes + kStageChunk - 1) / kStageChunk;
+    const int nThreads = (int)std::min<size_t>(kStageThreads, nChunks);
+    std::vector<cudaError_t> err(nThreads, cudaSuccess);
+    auto work = [&](int t) {
+        cudaSetDevice(ctx->device);
+        StageWorker& w = sp->w[t];
+        cudaError_t e = cudaSuccess;
+        size_t pending[2] = {0, 0}, pendingOff[2] = {0, 0};      // D2H: bytes waiting in buffer b
+        int use = 0;
+        for (size_t k = t; k < nChunks && e == cudaSuccess; k += nThreads, use ^= 1) {
+            const size_t off = k * kStageChunk, n = std::min(kStageChunk, bytes - off);
+            if (toDevice) {
+                e = cudaEventSynchronize(w.ev[use]);             // the copy that last used this buffer is done
+                if (e != cudaSuccess) break;
+                memcpy(w.buf[use], src + off, n);
+                e = cudaMemcpyAsync(dst + off, w.buf[use], n, cudaMemcpyHostToDevice, w.stream);
+                if (e == cudaSuccess) e = cudaEventRecord(w.ev[use], w.stream);
+            } else {
+                if (pending[use]) {                              // drain the buffer before reusing it
+                    e = cudaEventSynchronize(w.ev[use]);
+                    if (e != cudaSuccess) break;
+                    memcpy(dst + pendingOff[use], w.buf[use], pending[use]);
+                }
+                e = cudaMemcpyAsync(w.buf[use], src + off, n, cudaMemcpyDeviceToHost, w.stream);
+                if (e == cudaSuccess) e = cudaEventRecord(w.ev[use], w.stream);
+                pending[use] = n;
+                pendingOff[use] = off;
+            }
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
+        if (!toDevice && e == cudaSuccess)
+            for (int b = 0; b < 2; b++) {
+                const int q = use ^ b;                           // older buffer first (order is irrelevant, both are complete)
+                if (pending[q]) memcpy(dst + pendingOff[q], w.buf[q], pending[q]);
+            }
+        err[t] = e;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nThreads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (cudaError_t e : err)
+        if (e != cudaSuccess) return cuda_fail(e, "staged copy", __FILE__, __LINE__);
+    return LDU_OK;
+}
+}  // namespace
+
+int copy_h2d(ldu_context* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!bytes) return LDU_OK;
+    if (bytes >= kStageMin && is_pageable(src))
+        return staged_copy(ctx, (unsigned char*)dst, (const unsigned char*)src, bytes, true);
+    LDU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LDU_OK;
+}
+
+int copy_d2h(ldu_context* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!bytes) return LDU_OK;
+    if (bytes >= kStageMin && is_pageable(dst))
+        return staged_copy(ctx, (unsigned char*)dst, (const unsigned char*)src, bytes, false);
+    LDU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LDU_OK;
+}
+
+void stage_free(ldu_context* ctx)
+{
+    StagePool* sp = reinterpret_cast<StagePool*>(ctx->stage);
+    if (!sp) return;
+    for (int t = 0; t < kStageThreads; t++) {
+        if (sp->w[t].stream) cudaStreamDestroy(sp->w[t].stream);
+        for (int b = 0; b < 2; b++) {
+            if (sp->w[t].ev[b]) cudaEventDestroy(sp->w[t].ev[b]);
+            if (sp->w[t].buf[b]) cudaFreeHost(sp->w[t].buf[b]);
+        }
+    }
+    delete sp;
+    ctx->stage = nullptr;
 }
 
 double* work_vec(ldu_matrix* m, int idx)
@@ -152,6 +285,7 @@ int ldu_context_destroy(ldu_context* ctx)
     }
     cudaFree(ctx->comm.d_peer);
     cudaFree(ctx->comm.window);
+    stage_free(ctx);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return LDU_OK;
@@ -509,11 +643,10 @@ int ldu_matrix_set_coeffs(ldu_matrix* m, const double* diag, const double* upper
     cudaStream_t st = m->ctx->stream;
     LDU_CUDA(cudaSetDevice(m->ctx->device));
     LDU_TRY(set_lower_storage(m, lower != nullptr));
-    LDU_CUDA(cudaMemcpyAsync(m->d_diag, diag, m->nCells * sizeof(double), cudaMemcpyHostToDevice, st));
+    LDU_TRY(copy_h2d(m->ctx, m->d_diag, diag, m->nCells * sizeof(double)));
     if (m->nFaces) {
-        LDU_CUDA(cudaMemcpyAsync(m->d_upper, upper, m->nFaces * sizeof(double), cudaMemcpyHostToDevice, st));
-        if (lower)
-            LDU_CUDA(cudaMemcpyAsync(m->d_lower, lower, m->nFaces * sizeof(double), cudaMemcpyHostToDevice, st));
+        LDU_TRY(copy_h2d(m->ctx, m->d_upper, upper, m->nFaces * sizeof(double)));
+        if (lower) LDU_TRY(copy_h2d(m->ctx, m->d_lower, lower, m->nFaces * sizeof(double)));
     }
     for (size_t i = 0; i < m->ifs.size(); i++) {
         const Interface& it = m->ifs[i];
@@ -531,6 +664,30 @@ int ldu_matrix_set_coeffs(ldu_matrix* m, const double* diag, const double* upper
     LDU_CUDA(cudaStreamSynchronize(st));
     m->diagonalOnly = (upper == nullptr && lower == nullptr);
     m->haveCoeffs = true;
+    m->haveIfCoeffs = true;
+    m->coefGen++;
+    return LDU_OK;
+}
+
+int ldu_matrix_set_interface_coeffs(ldu_matrix* m, const double* const* bouCoeffs, const double* const* intCoeffs)
+{
+    if (!m) return LDU_EINVAL;
+    LDU_CUDA(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    for (size_t i = 0; i < m->ifs.size(); i++) {
+        const Interface& it = m->ifs[i];
+        if (!it.n) continue;
+        if (!bouCoeffs || !intCoeffs || !bouCoeffs[i] || !intCoeffs[i]) {
+            set_error("ldu_matrix_set_interface_coeffs: interface coefficients missing");
+            return LDU_EINVAL;
+        }
+        LDU_CUDA(cudaMemcpyAsync(m->d_bou + it.offset, bouCoeffs[i], it.n * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+        LDU_CUDA(cudaMemcpyAsync(m->d_int + it.offset, intCoeffs[i], it.n * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+    }
+    LDU_CUDA(cudaStreamSynchronize(st));
+    m->haveIfCoeffs = true;
     m->coefGen++;
     return LDU_OK;
 }
@@ -538,7 +695,17 @@ int ldu_matrix_set_coeffs(ldu_matrix* m, const double* diag, const double* upper
 int ldu_matrix_set_coeffs_device(ldu_matrix* m, const double* d_diag, const double* d_upper,
                                  const double* d_lower)
 {
-    if (!m || !d_diag) return LDU_EINVAL;
+    if (!m || !d_diag || (m->nFaces && !d_upper)) {
+        set_error("ldu_matrix_set_coeffs_device: bad argument");
+        return LDU_EINVAL;
+    }
+    if (m->nIfFaces > 0 && !m->haveIfCoeffs) {
+        // the coupled rows would run on uninitialised boundary coefficients
+        set_error("ldu_matrix_set_coeffs_device: the matrix has coupled patches; give their coefficients first "
+                  "(ldu_matrix_set_interface_coeffs or ldu_matrix_set_coeffs)");
+        return LDU_EINVAL;
+    }
+    LDU_CUDA(cudaSetDevice(m->ctx->device));
     cudaStream_t st = m->ctx->stream;
     LDU_TRY(set_lower_storage(m, d_lower != nullptr));
     LDU_CUDA(cudaMemcpyAsync(m->d_diag, d_diag, m->nCells * sizeof(double), cudaMemcpyDeviceToDevice, st));

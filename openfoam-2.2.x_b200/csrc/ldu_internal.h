@@ -103,6 +103,9 @@ struct ldu_context {
     // pinned staging for scalar read-back
     ldu::SolverScalars* h_scalars = nullptr;
     ldu::Comm comm;
+    // pinned staging ring for large copies from / to PAGEABLE host memory (what an application's
+    // scalarFields are): kStageThreads workers x 2 chunks, each worker with its own stream
+    void* stage = nullptr;            // ldu::StagePool, context.cu
 };
 
 namespace ldu {
@@ -202,6 +205,7 @@ struct ldu_matrix {
     std::vector<double> lastHistory;
     // GAMG hierarchy
     std::vector<ldu::GamgLevel*> levels;
+    bool haveIfCoeffs = false;        // bouCoeffs / intCoeffs of the coupled patches have been given
     bool hierarchyValid = false;
     bool externalHierarchy = false;   // levels handed over through ldu_gamg_set_level: never rebuilt by the library
     bool precondHierarchyReady = false;   // GAMG-as-preconditioner: coarse coefficients current
@@ -235,7 +239,15 @@ struct GamgLevel {
 };
 
 // ---- helpers implemented across the .cu files -----------------------------
-double* work_vec(ldu_matrix* m, int idx);   // lazily allocated nCells-sized scratch
+double* work_vec(ldu_matrix* m, int idx);
+// host <-> device copies of whole fields through the C ABI.  Page-locked host memory (ldu_host_alloc,
+// cudaHostRegister) goes straight to the copy engine on the context's stream; pageable memory above
+// 1 MB is cut into chunks that several host threads stage through pinned buffers, each on its own
+// stream (a plain cudaMemcpy from pageable memory is one thread memcpy-ing into the driver's bounce
+// buffer).  Both return with the copy COMPLETE and ordered after earlier work on the context's stream.
+int copy_h2d(ldu_context* ctx, void* dst, const void* src, size_t bytes);
+int copy_d2h(ldu_context* ctx, void* dst, const void* src, size_t bytes);
+void stage_free(ldu_context* ctx);   // lazily allocated nCells-sized scratch
 int ensure_scalars(ldu_matrix* m);
 int build_schedules(ldu_matrix* m);
 

@@ -689,17 +689,10 @@ struct Staged {  // device copies of host fields for one call
     double* in(int slot, const double* h)
     {
         double* d = work_vec(m, slot);
-        if (d && h)
-            cudaMemcpyAsync(d, h, (size_t)m->nCells * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream);
+        if (d && h && copy_h2d(m->ctx, d, h, (size_t)m->nCells * sizeof(double)) != LDU_OK) return nullptr;
         return d;
     }
-    int out(double* h, const double* d)
-    {
-        if (cudaMemcpyAsync(h, d, (size_t)m->nCells * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream)
-            != cudaSuccess)
-            return LDU_ECUDA;
-        return cudaStreamSynchronize(m->ctx->stream) == cudaSuccess ? LDU_OK : LDU_ECUDA;
-    }
+    int out(double* h, const double* d) { return copy_d2h(m->ctx, h, d, (size_t)m->nCells * sizeof(double)); }
 };
 
 int check_matrix(ldu_matrix* m, const char* who)

@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "ldu_residual", "ldu_precondition", "ldu_smooth", "ldu_solve", "ldu_amul_device", "ldu_tmul_device",
     "ldu_solve_device", "ldu_residual_history", "ldu_gamg_build", "ldu_gamg_nlevels",
     "ldu_gamg_level_sizes", "ldu_gamg_level_restrict", "ldu_gamg_level_coeffs", "ldu_controls_default",
-    "ldu_gamg_begin_levels", "ldu_gamg_set_level", "ldu_gamg_end_levels", "ldu_gamg_internal_levels",
+    "ldu_matrix_set_interface_coeffs", "ldu_gamg_begin_levels", "ldu_gamg_set_level", "ldu_gamg_end_levels", "ldu_gamg_internal_levels",
 ]
 
 
@@ -89,6 +89,7 @@ def library():
         L.ldu_matrix_destroy.argtypes = [vp]
         L.ldu_matrix_set_coeffs.argtypes = [vp, vp, vp, vp, vp, vp]
         L.ldu_matrix_set_coeffs_device.argtypes = [vp, vp, vp, vp]
+        L.ldu_matrix_set_interface_coeffs.argtypes = [vp, vp, vp]
         L.ldu_matrix_set_face_weights.argtypes = [vp, vp]
         L.ldu_amul.argtypes = [vp, vp, vp]
         L.ldu_tmul.argtypes = [vp, vp, vp]
@@ -381,6 +382,17 @@ class lduMatrix:
                "ldu_matrix_set_coeffs")
         self._symmetric = lower is None
 
+    def set_interface_coeffs(self, bouCoeffs, intCoeffs):
+        """boundary coefficients of the coupled patches alone (host arrays), for matrices whose diag/upper/lower
+        are handed over on the device"""
+        n_if = len(self.interfaces)
+        bou = [_f64(b) for b in bouCoeffs]
+        inc = [_f64(b) for b in intCoeffs]
+        assert len(bou) == n_if and len(inc) == n_if
+        bp = (C.c_void_p * max(n_if, 1))(*[b.ctypes.data for b in bou])
+        ip = (C.c_void_p * max(n_if, 1))(*[b.ctypes.data for b in inc])
+        _check(self.L.ldu_matrix_set_interface_coeffs(self.h, bp, ip), "ldu_matrix_set_interface_coeffs")
+
     def set_coeffs_device(self, d_diag: DeviceField, d_upper: DeviceField, d_lower: DeviceField | None = None):
         _check(self.L.ldu_matrix_set_coeffs_device(self.h, d_diag.ptr, d_upper.ptr,
                                                    None if d_lower is None else d_lower.ptr),
@@ -444,6 +456,9 @@ class lduMatrix:
 
     def Tmul_device(self, d_Tpsi: DeviceField, d_psi: DeviceField):
         _check(self.L.ldu_tmul_device(self.h, d_Tpsi.ptr, d_psi.ptr), "ldu_tmul_device")
+
+    def H_device(self, d_Hpsi: DeviceField, d_psi: DeviceField):
+        _check(self.L.ldu_H_device(self.h, d_Hpsi.ptr, d_psi.ptr), "ldu_H_device")
 
     def residual_history(self, cap=4096) -> np.ndarray:
         buf = np.zeros(cap)
