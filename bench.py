@@ -500,6 +500,184 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# --------------------------------------------------------------------------- #
+# second workload: GAMG (BASELINE configs 3 and 5)
+# --------------------------------------------------------------------------- #
+GAMG_METRIC = "GAMG V-cycles/sec (fp64, GaussSeidel smoother) on a ~2M-cell mesh"
+GAMG_UNIT = "V-cycles/s"
+
+
+def gamg_controls(smoother, **kw):
+    """the p solver of the simpleFoam tutorials (pitzDaily / motorBike system/fvSolution:19-31)"""
+    d = dict(solver="GAMG", smoother=smoother, agglomerator="faceAreaPair", nCellsInCoarsestLevel=10, mergeLevels=1,
+             cacheAgglomeration=True, nPreSweeps=0, nPostSweeps=2, nFinestSweeps=2)
+    d.update(kw)
+    return d
+
+
+def gamg_mesh(name):
+    """box128: 128^3 hex box (2,097,152 cells, the 3-D stand-in for a ~2M-cell case); sheet1448: 1448 x 1448 x 1
+    (2,096,704 cells: pitzDaily is 2-D, one cell thick); boxN / sheetN for other sizes"""
+    if name.startswith("sheet"):
+        n = int(name[5:])
+        return n, n, 1
+    n = int(name[3:])
+    return n, n, n
+
+
+def gamg_region(shape, rank, world):
+    from ldub200 import meshes, decompose
+    nx, ny, nz = shape
+    if world == 1:
+        s = meshes.laplacian_system(nx, ny, nz)
+        s["interfaces"] = []
+        return s
+    if not (nx == ny == nz):
+        raise SystemExit("the multi-GPU GAMG workload is the cubic box (decompose.local_box_region)")
+    return decompose.local_box_region(nx, rank, world)
+
+
+def reference_gamg(shape, ctl, cores, cycles):
+    """(V-cycles/s, iterations of the tolerance-driven solve or None) of the unmodified reference on `cores` cores:
+    cores == 1 the plain single-rank reference, else the box cut into `cores` regions, one coupled process each"""
+    from oracle import oracle as O
+    txt = O.dict_text(dict(ctl, agglomerator="weightedPair"))    # = faceAreaPair on this mesh (oracle/ref_driver.C)
+    if cores == 1:
+        s = gamg_region(shape, 0, 1)
+        s = {k: v for k, v in s.items() if k != "interfaces"}
+        _, so = O.ref_run(s, "time_iters", txt, 2, 2 + cycles)
+    else:
+        blocks = [gamg_region(shape, r, cores) for r in range(cores)]
+        _, so = O.ref_run_par(blocks, "time_iters", txt, 2, 2 + cycles)
+    t = [x for x in so.splitlines() if x.startswith("ITERS")][0].split()
+    ia, ta, ib, tb = int(t[1]), float(t[2]), int(t[3]), float(t[4])
+    return (ib - ia) / (tb - ta)
+
+
+def measure_gamg(ldub200, torch, ctx, stream, dist, shape, rank, world, smoothers, cycles, barrier, with_reference):
+    """V-cycle time of our GAMG (difference of two fixed-cycle solves: set-up and prologue cancel), the iteration
+    count of a tolerance-driven solve per smoother, and (rank 0, N = 1) the reference beside it."""
+    reg = gamg_region(shape, rank, world)
+    nC = reg["nCells"]
+    ifs = [ldub200.lduInterface(it["faceCells"], it["nbrRegion"], it["nbrInterface"]) for it in reg["interfaces"]]
+    A = ldub200.lduMatrix(ctx, nC, reg["lower"], reg["upper"], ifs)
+    A.set_coeffs(reg["diag"], reg["upperCoef"], None, [it["bouCoeffs"] for it in reg["interfaces"]],
+                 [it["intCoeffs"] for it in reg["interfaces"]])
+    A.set_face_weights(reg["faceWeights"])
+    d_psi = ldub200.DeviceField(ctx, nC)
+    d_src = ldub200.DeviceField(ctx, nC, reg["source"])
+    out = {"cells": int(np.prod(shape)), "regions": world, "settings": "GAMG, faceAreaPair, nCellsInCoarsestLevel 10, "
+           "mergeLevels 1, nPreSweeps 0, nPostSweeps 2, nFinestSweeps 2 (simpleFoam tutorials)", "smoothers": {}}
+
+    def timed_solve(ctl):
+        solver = ldub200.lduMatrix.solver.New("p", A, ctl)
+        best = None
+        for _ in range(3):
+            d_psi.zero()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            perf = solver.solve_device(d_psi, d_src)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if dist is not None:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            best = ms if best is None else min(best, ms)
+        return best, perf
+
+    for sm in smoothers:
+        l0 = ldub200.launch_count()
+        ms_a, _ = timed_solve(gamg_controls(sm, tolerance=0, relTol=0, maxIter=2))
+        ms_b, perf_b = timed_solve(gamg_controls(sm, tolerance=0, relTol=0, maxIter=2 + cycles))
+        ms_cycle = (ms_b - ms_a) / cycles
+        _, perf_tol = timed_solve(gamg_controls(sm, tolerance=1e-7, relTol=0, maxIter=200))
+        out["smoothers"][sm] = {"ms_per_vcycle": ms_cycle, "vcycles_per_s": 1e3 / ms_cycle,
+                                "levels": len(A.gamg_levels(gamg_controls(sm))) if world == 1 else None,
+                                "iterations_to_1e-7": int(perf_tol.nIterations),
+                                "final_residual": perf_tol.finalResidual,
+                                "residual_after_%d_cycles" % (2 + cycles): perf_b.finalResidual}
+    if with_reference and rank == 0:
+        try:
+            from oracle import oracle as O
+            ctl = gamg_controls("GaussSeidel")
+            ref_cycles = 6
+            r1 = reference_gamg(shape, ctl, 1, ref_cycles)
+            out["reference"] = {"single_rank": {"vcycles_per_s": r1, "cores": 1}}
+            s1 = gamg_region(shape, 0, 1)
+            s1 = {k: v for k, v in s1.items() if k != "interfaces"}
+            _, so = O.ref_run(s1, "solve", O.dict_text(dict(gamg_controls("GaussSeidel", tolerance=1e-7, relTol=0,
+                                                                          maxIter=200), agglomerator="weightedPair")))
+            pr = O.parse_perf(so)
+            out["reference"]["iterations_to_1e-7"] = pr["nIterations"]
+            out["reference"]["final_residual"] = pr["finalResidual"]
+            cores = reference_cores()
+            if cores > 1 and shape[0] == shape[1] == shape[2]:
+                out["reference"]["all_cores"] = {"vcycles_per_s": reference_gamg(shape, ctl, cores, ref_cycles),
+                                                 "cores": cores}
+        except Exception as e:
+            out["reference"] = {"failed": str(e)[:300]}
+    A.destroy()
+    return out
+
+
+def run_gamg(args):
+    import torch
+    import ldub200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    ctx = ldub200.Context(local_rank, stream.cuda_stream)
+    shape = gamg_mesh(args.gamg_mesh)
+    if world > 1:
+        ctx.connect_torch_distributed(8, int(shape[0] * shape[0]))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    res = measure_gamg(ldub200, torch, ctx, stream, dist, shape, rank, world,
+                       ["GaussSeidel", "multiColourGaussSeidel"], args.gamg_cycles, barrier,
+                       with_reference=(world == 1 and not args.no_cpu_baseline))
+    clocks = sampler.stop() if rank == 0 else None
+    lex, mc = res["smoothers"]["GaussSeidel"], res["smoothers"]["multiColourGaussSeidel"]
+    line = {"metric": GAMG_METRIC, "value": mc["vcycles_per_s"], "unit": GAMG_UNIT, "n_gpus": world,
+            "steps": args.gamg_cycles, "warmup": 2, "ms_per_step": mc["ms_per_vcycle"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.gamg_mesh} GAMG, {res['cells']} cells", "regions": world,
+                       "smoother": "multiColourGaussSeidel (value); GaussSeidel = the reference's lexicographic "
+                                   "smoother, bit-identical path, beside it"},
+            "gamg": res, "clocks": clocks, "gpu_launches": int(ldub200.launch_count())}
+    if "reference" in res and "single_rank" in res["reference"]:
+        best = res["reference"].get("all_cores", res["reference"]["single_rank"])
+        line["cpu_baseline"] = {"value": best["vcycles_per_s"], "unit": GAMG_UNIT, "cores": best["cores"],
+                                "kind": "reference", "sample": "6 steady-state V-cycles (difference of two "
+                                "fixed-cycle solves) of the same mesh and settings, lexicographic GaussSeidel"}
+        line["parity"] = {"iterations_to_1e-7": {"reference": res["reference"].get("iterations_to_1e-7"),
+                                                 "GaussSeidel": lex["iterations_to_1e-7"],
+                                                 "multiColourGaussSeidel": mc["iterations_to_1e-7"]}}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -512,9 +690,15 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=50, help="reference iterations timed per step")
     ap.add_argument("--no-parity", action="store_true", help="skip the reference run behind the parity object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pcg", choices=["pcg", "gamg"],
+                    help="pcg: the headline (BASELINE metric); gamg: V-cycles/s on a ~2M-cell mesh (configs 3, 5)")
+    ap.add_argument("--gamg-mesh", default="box128", help="box<N> (N^3 hex box) or sheet<N> (N x N x 1, 2-D)")
+    ap.add_argument("--gamg-cycles", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "gamg":
+        run_gamg(args)
     else:
         run_ours(args)
 

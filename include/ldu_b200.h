@@ -43,7 +43,13 @@ enum { LDU_PRECOND_NONE = 0, LDU_PRECOND_DIAGONAL = 1, LDU_PRECOND_DIC = 2,
 /* smoothers: matrices/lduMatrix/smoothers/ */
 enum { LDU_SMOOTHER_GS = 0, LDU_SMOOTHER_SYMGS = 1, LDU_SMOOTHER_DIC = 2,
        LDU_SMOOTHER_DILU = 3, LDU_SMOOTHER_DICGS = 4, LDU_SMOOTHER_DILUGS = 5,
-       LDU_SMOOTHER_FDIC = 6, LDU_SMOOTHER_NBGS = 7 };
+       LDU_SMOOTHER_FDIC = 6, LDU_SMOOTHER_NBGS = 7,
+       /* `smoother multiColourGaussSeidel;` -- an EXTENSION, not a reference smoother: GaussSeidelSmoother.C:66-187
+        * with the cells of every matrix (every GAMG level its own) visited colour by colour of a greedy colouring
+        * instead of in cell order, all cells of a colour in parallel.  It is the reference's Gauss-Seidel on the
+        * mesh renumbered by colour (ldu_colour_order): other iterates than the lexicographic smoother, same
+        * smoothing property; the dependency chain of a sweep is the number of colours (2 on a hex box). */
+       LDU_SMOOTHER_MCGS = 8 };
 
 /*
  * Solver controls = the keys the reference's solver constructors read from the

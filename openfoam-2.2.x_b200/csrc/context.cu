@@ -188,6 +188,45 @@ int ensure_scalars(ldu_matrix* m)
     return LDU_OK;
 }
 
+// greedy first-fit colouring of the cell graph in cell order (ldu_colour_order, multiColourGaussSeidel)
+int greedy_colouring(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr, std::vector<int>& colour,
+                     int* nColours)
+{
+    // CSR adjacency (both directions)
+    std::vector<int> start(nCells + 1, 0);
+    for (int f = 0; f < nFaces; f++) {
+        const int l = lowerAddr[f], u = upperAddr[f];
+        if (l < 0 || u < 0 || l >= nCells || u >= nCells || l == u) {
+            set_error("colouring: addressing out of range");
+            return LDU_EINVAL;
+        }
+        start[l + 1]++;
+        start[u + 1]++;
+    }
+    for (int c = 0; c < nCells; c++) start[c + 1] += start[c];
+    std::vector<int> adj(start[nCells]), fill(start.begin(), start.end() - 1);
+    for (int f = 0; f < nFaces; f++) {
+        adj[fill[lowerAddr[f]]++] = upperAddr[f];
+        adj[fill[upperAddr[f]]++] = lowerAddr[f];
+    }
+    colour.assign(nCells, -1);
+    std::vector<int> mark;
+    int nc = 0;
+    for (int c = 0; c < nCells; c++) {
+        mark.assign(nc + 1, 0);
+        for (int k = start[c]; k < start[c + 1]; k++) {
+            const int q = colour[adj[k]];
+            if (q >= 0) mark[q] = 1;
+        }
+        int q = 0;
+        while (q < nc && mark[q]) q++;
+        colour[c] = q;
+        if (q == nc) nc++;
+    }
+    *nColours = nc;
+    return LDU_OK;
+}
+
 }  // namespace ldu
 
 using namespace ldu;
@@ -602,6 +641,7 @@ int ldu_matrix_destroy(ldu_matrix* m)
     cudaFree(m->d_bRowStart);
     cudaFree(m->d_bEntry);
     cudaFree(m->d_cellBRow);
+    cudaFree(m->d_mcRows);
     cudaFree(m->d_ownerByNbrDesc);
     flow_free(m);
     stencil_free(m);
@@ -733,36 +773,9 @@ int ldu_colour_order(int nCells, int nFaces, const int* lowerAddr, const int* up
         set_error("ldu_colour_order: bad argument");
         return LDU_EINVAL;
     }
-    // CSR adjacency (both directions)
-    std::vector<int> start(nCells + 1, 0);
-    for (int f = 0; f < nFaces; f++) {
-        const int l = lowerAddr[f], u = upperAddr[f];
-        if (l < 0 || u < 0 || l >= nCells || u >= nCells || l == u) {
-            set_error("ldu_colour_order: addressing out of range");
-            return LDU_EINVAL;
-        }
-        start[l + 1]++;
-        start[u + 1]++;
-    }
-    for (int c = 0; c < nCells; c++) start[c + 1] += start[c];
-    std::vector<int> adj(start[nCells]), fill(start.begin(), start.end() - 1);
-    for (int f = 0; f < nFaces; f++) {
-        adj[fill[lowerAddr[f]]++] = upperAddr[f];
-        adj[fill[upperAddr[f]]++] = lowerAddr[f];
-    }
-    std::vector<int> colour(nCells, -1), mark;
+    std::vector<int> colour;
     int nc = 0;
-    for (int c = 0; c < nCells; c++) {
-        mark.assign(nc + 1, 0);
-        for (int k = start[c]; k < start[c + 1]; k++) {
-            const int q = colour[adj[k]];
-            if (q >= 0) mark[q] = 1;
-        }
-        int q = 0;
-        while (q < nc && mark[q]) q++;
-        colour[c] = q;
-        if (q == nc) nc++;
-    }
+    LDU_TRY(ldu::greedy_colouring(nCells, nFaces, lowerAddr, upperAddr, colour, &nc));
     // stable counting sort by colour
     std::vector<int> first(nc + 1, 0);
     for (int c = 0; c < nCells; c++) first[colour[c] + 1]++;

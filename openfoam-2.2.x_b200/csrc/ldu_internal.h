@@ -182,6 +182,9 @@ struct ldu_matrix {
     int* d_ownerByNbrDesc = nullptr;   // [nFaces] faces of each owner range by descending neighbour (lazy)
     int ifBlockStart = 0;          // first cell on any interface (nonBlockingGaussSeidelSmoother.C:66-81)
     int* d_cellBRow = nullptr;     // [nCells] boundary row of a cell or -1 (lazy, nonBlockingGaussSeidel only)
+    // multiColourGaussSeidel (sweeps.cu): rows grouped by greedy colour (lazy)
+    int* d_mcRows = nullptr;
+    std::vector<int> mcStart;      // [nColours+1]
     // sweep schedules (lazy)
     ldu::Schedule fwd, bwd;
     bool haveSchedules = false;
@@ -249,6 +252,8 @@ int copy_h2d(ldu_context* ctx, void* dst, const void* src, size_t bytes);
 int copy_d2h(ldu_context* ctx, void* dst, const void* src, size_t bytes);
 void stage_free(ldu_context* ctx);   // lazily allocated nCells-sized scratch
 int ensure_scalars(ldu_matrix* m);
+int greedy_colouring(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr, std::vector<int>& colour,
+                     int* nColours);
 int build_schedules(ldu_matrix* m);
 
 // kernels.cu

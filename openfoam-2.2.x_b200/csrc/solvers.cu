@@ -352,6 +352,7 @@ int smoother_setup(ldu_matrix* m, int kind, Smoother& s)
     case LDU_SMOOTHER_GS:
     case LDU_SMOOTHER_SYMGS:
     case LDU_SMOOTHER_NBGS:
+    case LDU_SMOOTHER_MCGS:
         return LDU_OK;
     case LDU_SMOOTHER_DIC:
     case LDU_SMOOTHER_DICGS:
@@ -384,6 +385,23 @@ static int gs_apply(ldu_matrix* m, double* psi, const double* source, int nSweep
             bPrime = bp;
         }
         LDU_TRY(gs_sweep(m, bPrime, sym ? work_vec(m, W_BLOWER) : nullptr, psi, sym));
+    }
+    return LDU_OK;
+}
+
+// multiColourGaussSeidel (extension, include/ldu_b200.h LDU_SMOOTHER_MCGS): the boundary treatment of GaussSeidel
+// (bPrime = source + Jacobi-coupled interface terms), the cells colour by colour
+static int mcgs_apply(ldu_matrix* m, double* psi, const double* source, int nSweeps)
+{
+    for (int sweep = 0; sweep < nSweeps; sweep++) {
+        const double* bPrime = source;
+        if (m->nIfFaces) {
+            double* bp = work_vec(m, W_BPRIME);
+            LDU_TRY(launch_map<true>(m, m->nCells, CopyMap{bp, source}));
+            LDU_TRY(k_interfaces(m, bp, psi, 0, -1.0, true));
+            bPrime = bp;
+        }
+        LDU_TRY(mcgs_sweep(m, bPrime, psi));
     }
     return LDU_OK;
 }
@@ -428,6 +446,8 @@ int smoother_apply(ldu_matrix* m, const Smoother& s, double* psi, const double* 
         return gs_apply(m, psi, source, nSweeps, false);
     case LDU_SMOOTHER_NBGS:
         return nbgs_apply(m, psi, source, nSweeps);
+    case LDU_SMOOTHER_MCGS:
+        return mcgs_apply(m, psi, source, nSweeps);
     case LDU_SMOOTHER_SYMGS:
         return gs_apply(m, psi, source, nSweeps, true);
     case LDU_SMOOTHER_DIC:

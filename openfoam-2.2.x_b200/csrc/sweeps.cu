@@ -414,6 +414,62 @@ int gs_sweep(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, b
     return LDU_OK;
 }
 
+// multiColourGaussSeidel: one colour of the greedy colouring per launch.  No cell of a colour has a neighbour of
+// that colour, so the rows of a launch are independent; a row uses the current values of all its neighbours and
+// performs the operations of the reference's row (GaussSeidelSmoother.C:151-176): bPrime, minus the lower-side
+// terms in ascending face order, minus the upper-side terms in ascending face order, divided by the diagonal.
+__global__ void __launch_bounds__(kBlock) mcgs_colour_kernel(
+    const SolverScalars* S, const int* __restrict__ rows, int nRows, const int* __restrict__ losortStart,
+    const int* __restrict__ losort, const int* __restrict__ lowerCol, const int* __restrict__ ownerStart,
+    const int* __restrict__ u, const double* __restrict__ diag, const double* __restrict__ upper,
+    const double* __restrict__ lower, const double* __restrict__ bPrime, double* __restrict__ psi)
+{
+    if (S->done) return;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nRows) return;
+    const int c = rows[i];
+    double acc = bPrime[c];
+    for (int k = losortStart[c]; k < losortStart[c + 1]; k++)
+        acc = __dsub_rn(acc, __dmul_rn(lower[losort[k]], psi[lowerCol[k]]));
+    for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) acc = __dsub_rn(acc, __dmul_rn(upper[f], psi[u[f]]));
+    psi[c] = __ddiv_rn(acc, diag[c]);
+}
+
+static int build_colours(ldu_matrix* m)
+{
+    if (m->d_mcRows) return LDU_OK;
+    std::vector<int> colour;
+    int nc = 0;
+    LDU_TRY(greedy_colouring(m->nCells, m->nFaces, m->h_l.data(), m->h_u.data(), colour, &nc));
+    // rows sorted by (colour, cell): stable counting sort
+    m->mcStart.assign(nc + 1, 0);
+    for (int c = 0; c < m->nCells; c++) m->mcStart[colour[c] + 1]++;
+    for (int q = 0; q < nc; q++) m->mcStart[q + 1] += m->mcStart[q];
+    std::vector<int> rows(std::max(m->nCells, 1)), fill(m->mcStart.begin(), m->mcStart.end() - 1);
+    for (int c = 0; c < m->nCells; c++) rows[fill[colour[c]]++] = c;
+    LDU_CUDA(cudaMalloc((void**)&m->d_mcRows, rows.size() * sizeof(int)));
+    LDU_CUDA(cudaMemcpyAsync(m->d_mcRows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice,
+                             m->ctx->stream));
+    LDU_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return LDU_OK;
+}
+
+int mcgs_sweep(ldu_matrix* m, const double* bPrime, double* psi)
+{
+    LDU_TRY(build_colours(m));
+    cudaStream_t st = m->ctx->stream;
+    for (size_t q = 0; q + 1 < m->mcStart.size(); q++) {
+        const int start = m->mcStart[q], nRows = m->mcStart[q + 1] - start;
+        if (nRows <= 0) continue;
+        mcgs_colour_kernel<<<(nRows + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+            m->d_scalars, m->d_mcRows + start, nRows, m->d_losortStart, m->d_losort, m->d_lowerCol, m->d_ownerStart,
+            m->d_u, m->d_diag, m->d_upper, m->d_lower, bPrime, psi);
+        count_launch();
+    }
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
 int nbgs_sweep(ldu_matrix* m, const double* source, double* psi)
 {
     LDU_TRY(build_schedules(m));

@@ -18,6 +18,8 @@ int calc_reciprocal_D(ldu_matrix* m, double* rD, bool dilu);
 int calc_reciprocal_diag(ldu_matrix* m, double* rD);
 int calc_fdic_coeffs(ldu_matrix* m, const double* rD, double* rDuUpper, double* rDlUpper);
 int gs_sweep(ldu_matrix* m, const double* bPrime, double* bLower, double* psi, bool sym);
+// one multiColourGaussSeidel sweep: colours in order, the rows of a colour in one launch
+int mcgs_sweep(ldu_matrix* m, const double* bPrime, double* psi);
 // one nonBlockingGaussSeidel sweep of a region WITH interfaces; m->d_recv already holds the halo
 int nbgs_sweep(ldu_matrix* m, const double* source, double* psi);
 

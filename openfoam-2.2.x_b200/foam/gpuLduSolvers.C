@@ -427,6 +427,7 @@ int smootherKind(const word& name)
     if (name == "GaussSeidel") return LDU_SMOOTHER_GS;
     if (name == "symGaussSeidel") return LDU_SMOOTHER_SYMGS;
     if (name == "nonBlockingGaussSeidel") return LDU_SMOOTHER_NBGS;
+    if (name == "multiColourGaussSeidel") return LDU_SMOOTHER_MCGS;   // extension, see ldu_b200.h
     if (name == "DIC") return LDU_SMOOTHER_DIC;
     if (name == "DILU") return LDU_SMOOTHER_DILU;
     if (name == "FDIC") return LDU_SMOOTHER_FDIC;

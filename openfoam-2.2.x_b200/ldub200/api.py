@@ -12,7 +12,7 @@ _LIB = _HERE.parent / "csrc" / "libldu_b200.so"
 SOLVERS = {"PCG": 0, "PBiCG": 1, "smoothSolver": 2, "GAMG": 3, "diagonal": 4}
 PRECONDITIONERS = {"none": 0, "diagonal": 1, "DIC": 2, "FDIC": 3, "DILU": 4, "GAMG": 5}
 SMOOTHERS = {"GaussSeidel": 0, "symGaussSeidel": 1, "DIC": 2, "DILU": 3, "DICGaussSeidel": 4,
-             "DILUGaussSeidel": 5, "FDIC": 6, "nonBlockingGaussSeidel": 7}
+             "DILUGaussSeidel": 5, "FDIC": 6, "nonBlockingGaussSeidel": 7, "multiColourGaussSeidel": 8}
 HANDLE_BYTES = 64
 
 

@@ -712,6 +712,80 @@ static void gs_sweeps(orc_matrix* ms, int R, double** psi, double** source, int 
     free_fields(bPrime, R);
 }
 
+/* multiColourGaussSeidel -- NOT one of the reference's smoothers: the north star's parallel form of
+ * GaussSeidelSmoother.C:66-187.  The cells are coloured greedily in cell order (first colour no already
+ * coloured neighbour has: include/ldu_b200.h ldu_colour_order); a sweep visits the colours in order and,
+ * inside a colour, updates every cell from the CURRENT values of its neighbours (none has its colour):
+ *     psi_c = ((bPrime_c - sum_{lower faces, ascending} lower_f psi_l) - sum_{upper faces, ascending} upper_f psi_u)/diag_c
+ * with bPrime as in GaussSeidel (source + the Jacobi-coupled interface terms) and the row's operations in the
+ * order the reference's loop performs them on a row (lower-side terms as their cells were visited, then the
+ * upper side, then the division).  It IS the reference's Gauss-Seidel run on the mesh renumbered by colour
+ * (renumberMesh-style, ldub200/renumber.py): same iterates up to the rounding of the row sums
+ * (tests/test_multicolour_gs.py).  losort order = ascending face index of the faces whose upper cell is c. */
+static int* greedy_colours(const orc_matrix* m, int* nColours)
+{
+    int n = m->nCells, c, f, k, q, nc = 0;
+    int* colour = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int* start = (int*)calloc((size_t)n + 1, sizeof(int));
+    int* adj = (int*)malloc(sizeof(int) * (size_t)(2 * m->nFaces + 1));
+    int* fill = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+    char* mark = (char*)malloc((size_t)n + 1);
+    for (f = 0; f < m->nFaces; f++) { start[m->l[f] + 1]++; start[m->u[f] + 1]++; }
+    for (c = 0; c < n; c++) { start[c + 1] += start[c]; fill[c] = start[c]; colour[c] = -1; }
+    for (f = 0; f < m->nFaces; f++) { adj[fill[m->l[f]]++] = m->u[f]; adj[fill[m->u[f]]++] = m->l[f]; }
+    for (c = 0; c < n; c++) {
+        for (q = 0; q <= nc; q++) mark[q] = 0;
+        for (k = start[c]; k < start[c + 1]; k++) if (colour[adj[k]] >= 0) mark[colour[adj[k]]] = 1;
+        q = 0;
+        while (q < nc && mark[q]) q++;
+        colour[c] = q;
+        if (q == nc) nc++;
+    }
+    free(start); free(adj); free(fill); free(mark);
+    *nColours = nc;
+    return colour;
+}
+
+static void mcgs_sweeps(orc_matrix* ms, int R, double** psi, double** source, int nSweeps)
+{
+    double** bPrime = alloc_fields(ms, R);
+    int** colour = (int**)malloc(sizeof(int*) * (size_t)R);
+    int* nc = (int*)malloc(sizeof(int) * (size_t)R);
+    int** losortStart = (int**)malloc(sizeof(int*) * (size_t)R);
+    int sweep, r, c, f, k, q;
+    for (r = 0; r < R; r++) {
+        const orc_matrix* m = &ms[r];
+        colour[r] = greedy_colours(m, &nc[r]);
+        losortStart[r] = (int*)calloc((size_t)m->nCells + 1, sizeof(int));
+        for (f = 0; f < m->nFaces; f++) losortStart[r][m->u[f] + 1]++;
+        for (c = 0; c < m->nCells; c++) losortStart[r][c + 1] += losortStart[r][c];
+    }
+    for (sweep = 0; sweep < nSweeps; sweep++) {
+        for (r = 0; r < R; r++) memcpy(bPrime[r], source[r], sizeof(double) * (size_t)ms[r].nCells);
+        for (r = 0; r < R; r++) update_interfaces(ms, R, r, bPrime[r], psi, 0, -1.0);
+        for (r = 0; r < R; r++) {
+            const orc_matrix* m = &ms[r];
+            double* x = psi[r];
+            for (q = 0; q < nc[r]; q++) {
+                for (c = 0; c < m->nCells; c++) {
+                    double acc;
+                    if (colour[r][c] != q) continue;
+                    acc = bPrime[r][c];
+                    for (k = losortStart[r][c]; k < losortStart[r][c + 1]; k++) {
+                        f = m->losort[k];
+                        acc -= m->lower[f] * x[m->l[f]];
+                    }
+                    for (f = m->ownerStart[c]; f < m->ownerStart[c + 1]; f++) acc -= m->upper[f] * x[m->u[f]];
+                    x[c] = acc / m->diag[c];
+                }
+            }
+        }
+    }
+    for (r = 0; r < R; r++) { free(colour[r]); free(losortStart[r]); }
+    free(colour); free(nc); free(losortStart);
+    free_fields(bPrime, R);
+}
+
 /* DICSmoother.C:67-116 / DILUSmoother.C:67-119 / FDICSmoother.C:98-146 */
 static void dic_family_smooth(orc_matrix* ms, int R, double** psi, double** source,
                               int nSweeps, int kind)
@@ -767,6 +841,9 @@ static int smooth_levels(orc_matrix* ms, int R, int smoother, double** psi, doub
     case ORC_SMOOTHER_DILUGS:
         dic_family_smooth(ms, R, psi, source, nSweeps, ORC_SMOOTHER_DILU);
         gs_sweeps(ms, R, psi, source, nSweeps, 0, 0);
+        return 0;
+    case ORC_SMOOTHER_MCGS:
+        mcgs_sweeps(ms, R, psi, source, nSweeps);
         return 0;
     }
     return -1;
