@@ -682,13 +682,17 @@ int main(int argc, char* argv[])
         // timed separately, the difference removes construction + prologue
         const int a = atoi(argv[5]);
         const int b = atoi(argv[6]);
+        // optional 7th argument: the tolerance of the fixed-iteration solves.  0 (default) for the Krylov
+        // solvers; GAMG hands its tolerance to the coarsest-level solver (GAMGSolverSolve.C:430-487), which
+        // would then run its 1000 iterations per cycle: a tolerance no cycle count reaches is given instead
+        const double fixedTol = argc > 7 ? atof(argv[7]) : 0.0;
         double t[2];
         int its[2];
         for (int pass = 0; pass < 2; pass++)
         {
             dictionary d(dictFromText(argv[4]));
             d.add("maxIter", pass ? b : a, true);
-            d.add("tolerance", 0.0, true);
+            d.add("tolerance", fixedTol, true);
             d.add("relTol", 0.0, true);
             scalarField x(psi);
             clockTime timer;
