@@ -476,6 +476,18 @@ def run_ours(args):
         if rank == 0:
             line["parity"] = par
 
+    # ---- the second workload, compact (BASELINE configs 3/5; the full line: --workload gamg) ------------
+    if world == 1 and not args.no_gamg:
+        try:
+            g = measure_gamg(ldub200, torch, ctx, stream, dist, gamg_mesh(args.gamg_mesh), rank, world,
+                             ["GaussSeidel", "multiColourGaussSeidel"], args.gamg_cycles, barrier, with_reference=False)
+            g["note"] = ("GaussSeidel = the reference's lexicographic smoother (bit-identical path); "
+                         "multiColourGaussSeidel = the same sweep colour by colour, per GAMG level; reference "
+                         "V-cycles/s and iteration counts beside them: profiles/r02_gamg_*.json (--workload gamg)")
+            line["gamg"] = g
+        except Exception as e:
+            line["gamg"] = {"failed": str(e)[:300]}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             v, kind, spent, cores = reference_rate(n, args.precond, 2, 2 + args.ref_iters)
@@ -710,6 +722,7 @@ def main():
                     help="pcg: the headline (BASELINE metric); gamg: V-cycles/s on a ~2M-cell mesh (configs 3, 5)")
     ap.add_argument("--gamg-mesh", default="box128", help="box<N> (N^3 hex box) or sheet<N> (N x N x 1, 2-D)")
     ap.add_argument("--gamg-cycles", type=int, default=10)
+    ap.add_argument("--no-gamg", action="store_true", help="pcg workload: skip the compact GAMG measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

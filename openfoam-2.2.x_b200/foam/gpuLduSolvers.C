@@ -7,6 +7,8 @@
 #include "Switch.H"
 #include "processorLduInterface.H"
 #include "cyclicLduInterface.H"
+#include "cyclicLduInterfaceField.H"
+#include "processorLduInterfaceField.H"
 #include "PstreamReduceOps.H"
 #include "UIPstream.H"
 #include "UOPstream.H"
@@ -48,6 +50,55 @@ namespace Foam
         addgpuGAMGAsymMatrixConstructorToTable_;
     lduMatrix::solver::addasymMatrixConstructorToTable<gpuSmoothSolver>
         addgpuSmoothSolverAsymMatrixConstructorToTable_;
+
+    // smoothers: which table each reference smoother is in (GaussSeidelSmoother.C:34-39, DICSmoother.C:34-36,
+    // DILUSmoother.C:34-36, ...)
+    #define registerGpuSmoother(Class, sym, asym)                                                  \
+        defineTypeNameAndDebug(Class, 0);                                                         \
+        struct Class##Registrar                                                                   \
+        {                                                                                         \
+            Class##Registrar()                                                                    \
+            {                                                                                     \
+                if (sym)                                                                          \
+                {                                                                                 \
+                    static lduMatrix::smoother::addsymMatrixConstructorToTable<Class> s_;         \
+                }                                                                                 \
+                if (asym)                                                                         \
+                {                                                                                 \
+                    static lduMatrix::smoother::addasymMatrixConstructorToTable<Class> a_;        \
+                }                                                                                 \
+            }                                                                                     \
+        } Class##Registrar_
+    registerGpuSmoother(gpuGaussSeidelSmoother, true, true);
+    registerGpuSmoother(gpuSymGaussSeidelSmoother, true, true);
+    registerGpuSmoother(gpuNonBlockingGaussSeidelSmoother, true, true);
+    registerGpuSmoother(gpuMultiColourGaussSeidelSmoother, true, true);
+    registerGpuSmoother(gpuDICSmoother, true, false);
+    registerGpuSmoother(gpuFDICSmoother, true, false);
+    registerGpuSmoother(gpuDICGaussSeidelSmoother, true, false);
+    registerGpuSmoother(gpuDILUSmoother, false, true);
+    registerGpuSmoother(gpuDILUGaussSeidelSmoother, false, true);
+
+    #define registerGpuPreconditioner(Class, sym, asym)                                            \
+        defineTypeNameAndDebug(Class, 0);                                                         \
+        struct Class##Registrar                                                                   \
+        {                                                                                         \
+            Class##Registrar()                                                                    \
+            {                                                                                     \
+                if (sym)                                                                          \
+                {                                                                                 \
+                    static lduMatrix::preconditioner::addsymMatrixConstructorToTable<Class> s_;   \
+                }                                                                                 \
+                if (asym)                                                                         \
+                {                                                                                 \
+                    static lduMatrix::preconditioner::addasymMatrixConstructorToTable<Class> a_;  \
+                }                                                                                 \
+            }                                                                                     \
+        } Class##Registrar_
+    registerGpuPreconditioner(gpuDiagonalPreconditioner, true, true);
+    registerGpuPreconditioner(gpuDICPreconditioner, true, false);
+    registerGpuPreconditioner(gpuFDICPreconditioner, true, false);
+    registerGpuPreconditioner(gpuDILUPreconditioner, false, true);
 
     //- With LDU_GPU_OVERRIDE=1 the reference's own names are re-pointed at the
     //  GPU classes (HashTable::set replaces, insert would refuse a duplicate:
@@ -167,6 +218,23 @@ void findCoupledPatches
         if (!interfaces.set(patchi)) continue;
         const lduInterface& li = interfaces[patchi].interface();
         const labelUList& fc = A.lduAddr().patchAddr(patchi);
+        // a transforming couple (rotational cyclic / processorCyclic) scales the neighbour values of a
+        // vector or tensor COMPONENT by pow(diag(forwardT).component(cmpt), rank) (cyclicLduInterfaceField.H:108-122);
+        // the device interfaces are identity couples: right for scalars (rank 0) and untransformed patches only
+        if
+        (
+            (isA<cyclicLduInterfaceField>(interfaces[patchi])
+          && refCast<const cyclicLduInterfaceField>(interfaces[patchi]).doTransform()
+          && refCast<const cyclicLduInterfaceField>(interfaces[patchi]).rank() > 0)
+         || (isA<processorLduInterfaceField>(interfaces[patchi])
+          && refCast<const processorLduInterfaceField>(interfaces[patchi]).doTransform()
+          && refCast<const processorLduInterfaceField>(interfaces[patchi]).rank() > 0)
+        )
+        {
+            FatalErrorIn("gpuLduSolver::solve")
+                << "coupled patch " << patchi << " transforms the components of a vector/tensor field"
+                << " (rotational cyclic): not supported by the GPU solver" << exit(FatalError);
+        }
         if (isA<processorLduInterface>(li))
         {
             cp.nbrRank.append(refCast<const processorLduInterface>(li).neighbProcNo());
@@ -262,26 +330,68 @@ struct cachedMatrix
     ldu_matrix* m;
     label nCells;
     label nFaces;
+    // fingerprint of the addressing (sizes, coupled patches, 4096 evenly spaced owner/neighbour pairs): an
+    // lduAddressing destroyed and another one allocated at the same address must not inherit the device copy
+    unsigned long long fingerprint;
+    unsigned long long lastUse;
     // the GAMGAgglomeration (a MeshObject when cacheAgglomeration is on) whose levels the device holds
     const GAMGAgglomeration* agglomeration;
 };
 
+unsigned long long addressingFingerprint(const lduAddressing& addr, const coupledPatches& cp)
+{
+    unsigned long long h = 1469598103934665603ull;
+    #define LDU_MIX(v) h = (h ^ (unsigned long long)(v))*1099511628211ull
+    const labelUList& l = addr.lowerAddr();
+    const labelUList& u = addr.upperAddr();
+    LDU_MIX(addr.size());
+    LDU_MIX(l.size());
+    const label step = max(label(1), l.size()/4096);
+    for (label f = 0; f < l.size(); f += step) { LDU_MIX(l[f]); LDU_MIX(u[f]); }
+    if (l.size()) { LDU_MIX(l[l.size() - 1]); LDU_MIX(u[l.size() - 1]); }
+    forAll(cp.sizes, i)
+    {
+        LDU_MIX(cp.sizes[i]);
+        LDU_MIX(cp.nbrRank[i]);
+        if (cp.sizes[i]) { LDU_MIX(cp.faceCells[i][0]); LDU_MIX(cp.faceCells[i][cp.sizes[i] - 1]); }
+    }
+    #undef LDU_MIX
+    return h;
+}
+
 cachedMatrix& deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
 {
     static std::map<const lduAddressing*, cachedMatrix> cache;
+    static unsigned long long useClock = 0;
+    // the meshes of one application: its fvMesh(es) and, per GAMG agglomeration kept on a mesh, a couple of dozen
+    // coarse levels when the reference's own GAMG calls gpu smoothers.  Beyond that the least recently used go
+    // (serial runs only: creating a matrix is collective in a parallel run, eviction must not differ per rank)
+    const label maxCached = 96;
     const lduAddressing& addr = A.lduAddr();
     const label nCells = addr.size();
     const label nFaces = addr.lowerAddr().size();
+    const unsigned long long fp = addressingFingerprint(addr, cp);
 
     std::map<const lduAddressing*, cachedMatrix>::iterator it = cache.find(&addr);
     if (it != cache.end())
     {
-        if (it->second.nCells == nCells && it->second.nFaces == nFaces)
+        if (it->second.nCells == nCells && it->second.nFaces == nFaces && it->second.fingerprint == fp)
         {
+            it->second.lastUse = ++useClock;
             return it->second;
         }
-        ldu_matrix_destroy(it->second.m);   // mesh changed under the same address
+        ldu_matrix_destroy(it->second.m);   // another mesh under the same address
         cache.erase(it);
+    }
+    if (!Pstream::parRun() && label(cache.size()) >= maxCached)
+    {
+        std::map<const lduAddressing*, cachedMatrix>::iterator oldest = cache.begin();
+        for (it = cache.begin(); it != cache.end(); ++it)
+        {
+            if (it->second.lastUse < oldest->second.lastUse) oldest = it;
+        }
+        ldu_matrix_destroy(oldest->second.m);
+        cache.erase(oldest);
     }
 
     // index of the matching interface in the neighbour's (compact) list: each side
@@ -328,6 +438,8 @@ cachedMatrix& deviceMatrix(const lduMatrix& A, const coupledPatches& cp)
     c.nFaces = nFaces;
     c.m = NULL;
     c.agglomeration = NULL;
+    c.fingerprint = fp;
+    c.lastUse = ++useClock;
     check
     (
         ldu_matrix_create
@@ -407,6 +519,43 @@ void uploadAgglomeration
         delete &agg;          // GAMGSolver::~GAMGSolver, GAMGSolver.C:144-154
         cm.agglomeration = NULL;
     }
+}
+
+// addressing (cached) + this object's coefficients on the device
+cachedMatrix& uploadMatrix
+(
+    const lduMatrix& A,
+    const FieldField<Field, scalar>& interfaceBouCoeffs,
+    const FieldField<Field, scalar>& interfaceIntCoeffs,
+    const lduInterfaceFieldPtrsList& interfaces,
+    coupledPatches& cp
+)
+{
+    findCoupledPatches(A, interfaces, cp);
+    cachedMatrix& cm = deviceMatrix(A, cp);
+
+    // interfaceBouCoeffs_/interfaceIntCoeffs_ of the coupled patches (lduMatrix.H:97-104)
+    List<const double*> bou(cp.patchIDs.size()), intc(cp.patchIDs.size());
+    forAll(cp.patchIDs, i)
+    {
+        bou[i] = interfaceBouCoeffs[cp.patchIDs[i]].begin();
+        intc[i] = interfaceIntCoeffs[cp.patchIDs[i]].begin();
+    }
+    const bool hasUpper = A.hasUpper() || A.hasLower();
+    check
+    (
+        ldu_matrix_set_coeffs
+        (
+            cm.m,
+            A.diag().begin(),
+            hasUpper ? A.upper().begin() : NULL,
+            A.asymmetric() ? A.lower().begin() : NULL,
+            bou.size() ? bou.begin() : NULL,
+            intc.size() ? intc.begin() : NULL
+        ),
+        "ldu_matrix_set_coeffs"
+    );
+    return cm;
 }
 
 int preconditionerKind(const word& name)
@@ -553,8 +702,7 @@ Foam::solverPerformance Foam::gpuLduSolver::solve
     fillControls(c);
 
     coupledPatches cp;
-    findCoupledPatches(matrix_, interfaces_, cp);
-    cachedMatrix& cm = deviceMatrix(matrix_, cp);
+    cachedMatrix& cm = uploadMatrix(matrix_, interfaceBouCoeffs_, interfaceIntCoeffs_, interfaces_, cp);
     ldu_matrix* m = cm.m;
     if (c.solver == LDU_SOLVER_GAMG)
     {
@@ -567,28 +715,6 @@ Foam::solverPerformance Foam::gpuLduSolver::solve
             cm, matrix_, controlDict_.lookupEntry("preconditioner", false, false).dict(), cp
         );
     }
-
-    // interfaceBouCoeffs_/interfaceIntCoeffs_ of the coupled patches (lduMatrix.H:97-104)
-    List<const double*> bou(cp.patchIDs.size()), intc(cp.patchIDs.size());
-    forAll(cp.patchIDs, i)
-    {
-        bou[i] = interfaceBouCoeffs_[cp.patchIDs[i]].begin();
-        intc[i] = interfaceIntCoeffs_[cp.patchIDs[i]].begin();
-    }
-
-    check
-    (
-        ldu_matrix_set_coeffs
-        (
-            m,
-            matrix_.diag().begin(),
-            matrix_.upper().begin(),
-            matrix_.asymmetric() ? matrix_.lower().begin() : NULL,
-            bou.size() ? bou.begin() : NULL,
-            intc.size() ? intc.begin() : NULL
-        ),
-        "ldu_matrix_set_coeffs"
-    );
 
     ldu_solver_performance p;
     check(ldu_solve(m, &c, psi.begin(), source.begin(), &p), "ldu_solve");
@@ -604,6 +730,74 @@ Foam::solverPerformance Foam::gpuLduSolver::solve
         p.nIterations,
         p.converged,
         p.singular
+    );
+}
+
+
+// * * * * * * * * * * * * * smoothers / preconditioners * * * * * * * * * * * //
+
+Foam::gpuLduSmoother::gpuLduSmoother
+(
+    const word& fieldName,
+    const lduMatrix& matrix,
+    const FieldField<Field, scalar>& interfaceBouCoeffs,
+    const FieldField<Field, scalar>& interfaceIntCoeffs,
+    const lduInterfaceFieldPtrsList& interfaces
+)
+:
+    lduMatrix::smoother(fieldName, matrix, interfaceBouCoeffs, interfaceIntCoeffs, interfaces),
+    m_(NULL)
+{
+    coupledPatches cp;
+    m_ = uploadMatrix(matrix, interfaceBouCoeffs, interfaceIntCoeffs, interfaces, cp).m;
+}
+
+
+void Foam::gpuLduSmoother::smooth
+(
+    scalarField& psi,
+    const scalarField& source,
+    const direction,
+    const label nSweeps
+) const
+{
+    check
+    (
+        ldu_smooth(static_cast<ldu_matrix*>(m_), smootherKind(), psi.begin(), source.begin(), nSweeps),
+        "ldu_smooth"
+    );
+}
+
+
+Foam::gpuLduPreconditioner::gpuLduPreconditioner(const lduMatrix::solver& sol, const dictionary&)
+:
+    lduMatrix::preconditioner(sol),
+    m_(NULL)
+{
+    coupledPatches cp;
+    m_ = uploadMatrix
+    (
+        sol.matrix(), sol.interfaceBouCoeffs(), sol.interfaceIntCoeffs(), sol.interfaces(), cp
+    ).m;
+}
+
+
+void Foam::gpuLduPreconditioner::precondition(scalarField& wA, const scalarField& rA, const direction) const
+{
+    check
+    (
+        ldu_precondition(static_cast<ldu_matrix*>(m_), preconditionerKind(), wA.begin(), rA.begin(), 0),
+        "ldu_precondition"
+    );
+}
+
+
+void Foam::gpuLduPreconditioner::preconditionT(scalarField& wT, const scalarField& rT, const direction) const
+{
+    check
+    (
+        ldu_precondition(static_cast<ldu_matrix*>(m_), preconditionerKind(), wT.begin(), rT.begin(), 1),
+        "ldu_precondition"
     );
 }
 

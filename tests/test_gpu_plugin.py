@@ -211,3 +211,64 @@ def test_plugin_gamg_uses_the_references_own_agglomeration(ctl, gpu):
     assert "runs as algebraicPair" not in so_gpu
     assert a["nIterations"] == b["nIterations"] and a["finalResidual"] == b["finalResidual"]
     assert np.array_equal(psi_gpu, psi_ref)
+
+
+# --- the reference's other two tables of this path: lduMatrix::smoother and lduMatrix::preconditioner
+@pytest.mark.parametrize("name,cpu,gpu", [
+    ("box12_var", "GaussSeidel", "gpuGaussSeidel"),
+    ("box12_var", "symGaussSeidel", "gpuSymGaussSeidel"),
+    ("box12_var", "DIC", "gpuDIC"),
+    ("box12_var", "DICGaussSeidel", "gpuDICGaussSeidel"),
+    ("asym10", "DILU", "gpuDILU"),
+    ("asym10", "GaussSeidel", "gpuGaussSeidel"),
+])
+def test_gpu_smoothers_in_the_references_smoother_table(name, cpu, gpu):
+    """lduMatrix::smoother::New("p", A, ..., dict) with `smoother gpu<Name>;` (lduMatrix.H:262-400)"""
+    import numpy as np
+    if not (PLUGIN.exists() and O.ref_available()):
+        pytest.skip("plug-in / reference binaries not built")
+    s = cases.system(name)
+    x0 = np.sin(0.3 * np.arange(s["nCells"]))
+    ref, _ = O.ref_run(s, "smooth", O.dict_text(dict(smoother=cpu)), 3, psi=x0)
+    got, _ = O.ref_run(s, "smooth", O.dict_text(dict(smoother=gpu)), 3, psi=x0,
+                       extra_env=dict(LDU_REF_LIBS=str(PLUGIN)))
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("name,cpu,gpu", [("box12_var", "DIC", "gpuDIC"), ("box12_var", "FDIC", "gpuFDIC"),
+                                          ("asym10", "DILU", "gpuDILU"), ("box12_var", "diagonal", "gpuDiagonal")])
+def test_gpu_preconditioners_in_the_references_preconditioner_table(name, cpu, gpu):
+    """lduMatrix::preconditioner::New(solver, dict) with `preconditioner gpu<Name>;` (lduMatrix.H:402-506)"""
+    import numpy as np
+    if not (PLUGIN.exists() and O.ref_available()):
+        pytest.skip("plug-in / reference binaries not built")
+    s = cases.system(name)
+    ref, _ = O.ref_run(s, "precondition", cpu)
+    got, _ = O.ref_run(s, "precondition", gpu, extra_env=dict(LDU_REF_LIBS=str(PLUGIN)))
+    assert np.array_equal(got, ref)
+    if cpu == "DILU":
+        ref, _ = O.ref_run(s, "preconditionT", cpu)
+        got, _ = O.ref_run(s, "preconditionT", gpu, extra_env=dict(LDU_REF_LIBS=str(PLUGIN)))
+        assert np.array_equal(got, ref)
+
+
+def test_references_own_solvers_with_gpu_smoother_and_preconditioner():
+    """hybrid runs: the reference's CPU GAMG with `smoother gpuGaussSeidel` on every level, the reference's CPU PCG
+    with `preconditioner gpuDIC`: bit-identical to the all-CPU runs (the loops around are the reference's own)"""
+    import numpy as np
+    if not (PLUGIN.exists() and O.ref_available()):
+        pytest.skip("plug-in / reference binaries not built")
+    s = cases.system("box12_var")
+    env = dict(LDU_REF_LIBS=str(PLUGIN))
+    g = dict(solver="GAMG", smoother="GaussSeidel", agglomerator="algebraicPair", nCellsInCoarsestLevel=10,
+             mergeLevels=1, cacheAgglomeration=False, tolerance=1e-8, relTol=0)
+    psi_ref, so = O.ref_run(s, "solve", O.dict_text(g))
+    psi_gpu, so_gpu = O.ref_run(s, "solve", O.dict_text(dict(g, smoother="gpuGaussSeidel")), extra_env=env)
+    assert O.parse_perf(so_gpu)["nIterations"] == O.parse_perf(so)["nIterations"]
+    assert np.array_equal(psi_gpu, psi_ref)
+    p = dict(solver="PCG", preconditioner="DIC", tolerance=1e-9, relTol=0)
+    psi_ref, so = O.ref_run(s, "solve", O.dict_text(p))
+    psi_gpu, so_gpu = O.ref_run(s, "solve", O.dict_text(dict(p, preconditioner="gpuDIC")), extra_env=env)
+    a, b = O.parse_perf(so_gpu), O.parse_perf(so)
+    assert a["nIterations"] == b["nIterations"] and a["finalResidual"] == b["finalResidual"]
+    assert np.array_equal(psi_gpu, psi_ref)
