@@ -54,6 +54,7 @@
 // barrier + hand-off chain alone is 105.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "epilogue.cuh"
 #include "reduce.cuh"
@@ -807,6 +808,385 @@ __global__ void __launch_bounds__(64, 1) sweep3_kernel(S2Args a)
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Fourth generation: CHAINED register-stacked warps (LDU_STENCIL=4).
+//
+// What the trace of sweep3_kernel showed: a lone warp with 8 planes in its registers needs 0.57 us per tick (it
+// has nobody to hide its LDS / SHFL / STG / LDGSTS latencies behind), and every stack-to-stack hop through L2 costs
+// 3 us.  Here a CTA is a CHAIN of M such warps with W planes each (W = 2): warp q hands the result of its last
+// plane to warp q+1 through a ring of tagged 16-byte words in shared memory ({value, tick+1}; the consumer polls
+// its word, the producer throttles on the consumer's progress counter), so
+//   * a tick of a warp is ~90 instructions instead of ~350,
+//   * the M warps of a CTA run on different SM sub-partitions as a dataflow pipeline: no barrier,
+//   * a CTA covers M*W planes: only every (M*W)-th plane crosses CTAs through L2.
+// Layout, operand rings (cp.async, per warp), the helper warp that forwards the group's faces from L2 and the
+// arithmetic are those of sweep3_kernel with W3 = M*W planes per stack.
+// ---------------------------------------------------------------------------
+constexpr int kRing4 = 16;     // ticks of forwarded j-face words
+constexpr int kHand4 = 16;     // ticks of warp-to-warp hand-off words (also the ring of the stack's k-face words)
+constexpr int kD4 = 8;         // operand ring depth (ticks) of every warp
+
+template <int W, int M>
+struct Smem4 {
+    double ops[M][kD4][4][W][32];   // operand rings
+    LLW kx[M][kHand4][32];          // kx[q]: input words of pipeline warp q (q = 0: from the helper)
+    LLW hj[kRing4][M * W];          // helper -> all warps: j-face row of loop tick s in slot s % kRing4, tag s + 1
+    volatile int prog[M];           // ticks completed by pipeline warp q
+    volatile int abort;
+    int ticket;
+};
+
+template <int W, int M, bool BWD>
+__global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
+{
+    constexpr int MW = M * W;
+    extern __shared__ uint4 smem_raw[];
+    Smem4<W, M>* sm = reinterpret_cast<Smem4<W, M>*>(smem_raw);
+    if (a.guarded && a.S->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        sm->ticket = (int)atomicAdd(&a.ticket[0], 1u);
+        sm->abort = 0;
+    }
+    if (threadIdx.x < M) sm->prog[threadIdx.x] = 0;
+    {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);      // tags 0: never a valid tag
+        uint4* q0 = reinterpret_cast<uint4*>(&sm->kx[0][0][0]);
+        for (int q = threadIdx.x; q < M * kHand4 * 32 + kRing4 * MW; q += (M + 2) * 32) q0[q] = z;
+    }
+    __syncthreads();
+    const int tk = sm->ticket;
+
+    const int nx = a.b.nx, nJ = a.b.nJ, steps = a.b.steps, ticks = a.b.ticks, nKg = a.b.nKg;
+    const int nCta = nKg * nJ;
+    const int tr = BWD ? nCta - 1 - tk : tk;
+    const int kg = tr / nJ, J = tr - kg * nJ;
+    const int g = kg * nJ + J;
+    const int Wg = min(MW, a.b.nz - kg * MW);                  // planes of this stack that exist
+    const bool kIn = BWD ? (kg + 1 < nKg) : (kg > 0);
+    const bool kOut = BWD ? (kg > 0) : (kg + 1 < nKg);
+    const bool jIn = BWD ? (J + 1 < nJ) : (J > 0);
+    const bool jOut = BWD ? (J > 0) : (J + 1 < nJ);
+    const unsigned int epoch = a.epoch;
+    const int nRho = nx + MW - 1;                              // rows of a group's gJ block
+    auto sigma_of = [&](int s_) { return BWD ? ticks - 1 - s_ : s_; };
+    auto k_row = [&](int s_) -> int {
+        const int sg = sigma_of(s_);
+        const int t = BWD ? sg - (MW - 1) : sg;
+        return (kIn && t >= 0 && t < steps) ? t : -1;
+    };
+    auto j_row = [&](int s_) -> int {
+        const int sg = sigma_of(s_);
+        const int rho = BWD ? sg - 31 : sg;
+        return (jIn && rho >= 0 && rho < nRho) ? rho : -1;
+    };
+
+    if (warp >= M) {
+        // ------------------------------------------------------------------ helper warps
+        // warp M forwards the stack's k-face rows (32 words per tick, for chain warp 0), warp M+1 the column's
+        // j-face rows (M*W words per tick, for all warps): up to kPoll rows per L2 round trip each, so that a
+        // consumer that runs a few ticks behind its producer is never paced by the polling
+        constexpr int kPoll = 8;
+        const bool forK = (warp == M);
+        if (forK ? !kIn : !jIn) return;
+        const LLW* gIn = forK ? a.gK + ((long long)(BWD ? g + nJ : g - nJ) * steps) * 32 + lane
+                              : a.gJ + ((long long)(BWD ? g + 1 : g - 1) * nRho) * MW + (lane < MW ? lane : 0);
+        const unsigned int outA = forK ? (unsigned int)__cvta_generic_to_shared(&sm->kx[0][0][lane])
+                                       : (unsigned int)__cvta_generic_to_shared(&sm->hj[0][lane < MW ? lane : 0]);
+        const int rowWords = forK ? 32 : MW;
+        const unsigned int slotBytes = (unsigned int)rowWords * 16u;
+        const int ringMask = forK ? kHand4 - 1 : kRing4 - 1;
+        const bool mine = lane < rowWords;
+        int sn = 0;                                          // next loop tick to forward
+        long long tstart = 0;
+        for (int spin = 0; sn < ticks;) {
+            if (sm->abort) break;
+            int cap;
+            if (forK) {
+                cap = min(ticks, sm->prog[0] + kHand4 - 1);
+            } else {
+                int minProg = sm->prog[0];
+#pragma unroll
+                for (int w_ = 1; w_ < M; w_++) minProg = min(minProg, sm->prog[w_]);
+                cap = min(ticks, minProg + kRing4 - 1);
+            }
+            while (sn < cap && (forK ? k_row(sn) : j_row(sn)) < 0) sn++;
+            LLW w[kPoll];
+            int r[kPoll];
+#pragma unroll
+            for (int i = 0; i < kPoll; i++) {
+                r[i] = (sn + i < cap) ? (forK ? k_row(sn + i) : j_row(sn + i)) : -1;
+                if (r[i] >= 0 && mine) g_peek(gIn + (long long)r[i] * rowWords, w[i]);
+            }
+            bool did = false;
+#pragma unroll
+            for (int i = 0; i < kPoll; i++) {       // rows become valid in order
+                if (r[i] < 0 || !__all_sync(0xffffffffu, !mine || ok(w[i], epoch))) break;
+                if (mine) s_store_a(outA + (unsigned int)(sn & ringMask) * slotBytes, w[i].lo, w[i].hi, (unsigned int)sn + 1u);
+                sn++;
+                did = true;
+            }
+            if (did) {
+                spin = 0;
+                tstart = 0;
+            } else if ((++spin & 63) == 63) {
+                if (tstart == 0) tstart = clock64();
+                else if (clock64() - tstart > kTimeout2) {
+                    sm->abort = 1;
+                    a.S->commError = 2;
+                    a.S->done = 1;
+                    break;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- compute warps
+    // Everything a tick needs is a running pointer or a precomputed range of loop ticks: the tick is a chain of
+    // dependent instructions of ONE warp, every instruction saved is 5-10 cycles of the sweep's critical path.
+    const int q = BWD ? M - 1 - warp : warp;       // position in the chain: q = 0 takes the stack's k-face
+    const int p0 = warp * W;                       // first plane (layout index) of this warp
+    const int edgeLane = BWD ? 31 : 0, pubLane = BWD ? 0 : 31;
+    const bool last = (q == M - 1);
+    constexpr unsigned int kOpBytes = W * 256u, kSlotBytes = 4u * kOpBytes;
+    const int dSig = BWD ? -1 : 1;
+    const int sig0 = BWD ? ticks - 1 : 0;
+    const long long tickStride = (long long)dSig * (MW * 32);   // elements per tick in the stream
+    const long long elemBase = (long long)g * ticks * MW * 32 + (long long)p0 * 32 + (long long)sig0 * (MW * 32);
+    // operand streams of the NEXT tick to prefetch (advance by tickStride per tick)
+    const double* nPk = a.pk + elemBase + lane * 2;
+    const double* nPj = a.pj + elemBase + lane * 2;
+    const double* nPi = a.pi + elemBase + lane * 2;
+    const double* nY = a.Y + elemBase + lane * 2;
+    double* pY = a.Y + elemBase + lane;                         // result rows of the current tick
+    const unsigned int ring = (unsigned int)__cvta_generic_to_shared(&sm->ops[warp][0][0][0][0]) + (unsigned int)lane * 16u;
+    const double* ringP = &sm->ops[warp][0][0][0][lane];
+    const unsigned int inA = (unsigned int)__cvta_generic_to_shared(&sm->kx[q][0][lane]);
+    const unsigned int outA = (unsigned int)__cvta_generic_to_shared(&sm->kx[q + 1 < M ? q + 1 : q][0][lane]);
+    const unsigned int hjA = (unsigned int)__cvta_generic_to_shared(&sm->hj[0][p0]);
+    // loop-tick ranges (forward and backward alike: both run s = 0 .. ticks-1)
+    //   k input from the helper (q == 0): rows exist for s in [0, steps)       (k_row)
+    //   j input: s in [0, jEnd)                                               (j_row)
+    //   k output (last warp): step t = s - (MW-1) (fwd) / sigma (bwd) in [0, steps)
+    //   j output: rho = sigma - 31 (fwd) / sigma (bwd) in [0, nRho)
+    //   Y row of plane p: t = sigma - (p0+p) in [0, steps)
+    const int kInEnd = (q == 0) ? (kIn ? steps : 0) : ticks;    // q > 0: the word of warp q-1 (ticks 1..)
+    const int jInEnd = jIn ? (BWD ? ticks - 31 : nRho) : 0;
+    int yLo[W], yHi[W];
+#pragma unroll
+    for (int p = 0; p < W; p++) {
+        // forward: sigma = s, valid for s in [p0+p, p0+p+steps); backward: sigma = ticks-1-s
+        const int lo = p0 + p, hi = p0 + p + steps;             // sigma range
+        yLo[p] = BWD ? ticks - hi : lo;
+        yHi[p] = (p0 + p < Wg) ? (BWD ? ticks - lo : hi) : yLo[p];
+    }
+    // k output of the last warp: forward t = s - (MW-1) >= 0, < steps  -> s in [MW-1, MW-1+steps);
+    // backward t = sigma = ticks-1-s < steps -> s in [ticks-steps, ticks)
+    const int kOutLo = (last && kOut) ? (BWD ? ticks - steps : MW - 1) : 0;
+    const int kOutHi = (last && kOut) ? (BWD ? ticks : MW - 1 + steps) : 0;
+    LLW* gKout = a.gK + ((long long)g * steps) * 32 + lane + (long long)(BWD ? steps - 1 : 0) * 32 - (long long)kOutLo * dSig * 32;
+    // j output: forward rho = s - 31 in [0, nRho) -> s in [31, 31+nRho); backward rho = ticks-1-s in [0, nRho)
+    const int jOutLo = jOut ? (BWD ? ticks - nRho : 31) : 0;
+    const int jOutHi = jOut ? (BWD ? ticks : 31 + nRho) : 0;
+    LLW* gJout = a.gJ + ((long long)g * nRho) * MW + p0 + (long long)(BWD ? nRho - 1 : 0) * MW - (long long)jOutLo * dSig * MW;
+
+    unsigned long long* trace = a.trace ? a.trace + 8ull * ((unsigned int)tk * M + q) : nullptr;
+    const long long trStartC = clock64();
+    if (trace && lane == 0) {
+        trace[0] = ((unsigned long long)kg << 40) | ((unsigned long long)J << 20) | (unsigned int)q;
+        trace[1] = gtimer();
+    }
+    bool dead = false;
+    auto spin_fail = [&](long long c0) {     // warp-uniform time-out / abort test of a spin loop
+        bool bad = sm->abort != 0 || clock64() - c0 > kTimeout2;
+        return __any_sync(0xffffffffu, bad);
+    };
+    auto issue_next = [&](unsigned int slot) {
+        const unsigned int d = ring + slot * kSlotBytes;
+#pragma unroll
+        for (int c = 0; c < W / 2; c++) {
+            cp_async16(d + c * 512u, nPk + c * 64);
+            cp_async16(d + kOpBytes + c * 512u, nPj + c * 64);
+            cp_async16(d + 2u * kOpBytes + c * 512u, nPi + c * 64);
+            cp_async16(d + 3u * kOpBytes + c * 512u, nY + c * 64);
+        }
+        nPk += tickStride;
+        nPj += tickStride;
+        nPi += tickStride;
+        nY += tickStride;
+    };
+
+    double res[W];
+#pragma unroll
+    for (int p = 0; p < W; p++) res[p] = 0.0;
+    int nIssued = 0;
+#pragma unroll
+    for (int d_ = 0; d_ < kD4; d_++) {
+        if (nIssued < ticks) { issue_next((unsigned int)d_); nIssued++; }
+        cp_async_commit();
+    }
+
+    // The tick loop, compiled once per ROLE of the warp (what feeds it, what it feeds, whether its group has
+    // j-faces): a lone warp pays 15-20 cycles for every branch, also for a uniform, loop-invariant one
+    // (measured: the loop with everything but its control flow removed cost 500 of 820 cycles per tick).
+    //   RIN  0: no k input, 1: from the helper (stack below), 2: from warp q-1
+    //   ROUT 0: nothing, 1: hand-off to warp q+1, 2: the stack's k-face to L2
+    auto run = [&](auto RIN_, auto ROUT_, auto JI_, auto JO_) {
+        constexpr int RIN = decltype(RIN_)::value, ROUT = decltype(ROUT_)::value;
+        constexpr bool JI = decltype(JI_)::value, JO = decltype(JO_)::value;
+        unsigned int slot = 0;
+#pragma unroll 1
+        for (int s_ = 0; s_ < ticks; s_++) {
+            // ---- k input: from the helper (row of this tick, tag s+1) or from warp q-1 (its tick s-1, tag s)
+            double vkin = 0.0;
+            if (RIN == 1 ? (s_ < kInEnd) : (RIN == 2 && s_ > 0)) {
+                const unsigned int slotIn = (unsigned int)((RIN == 1 ? s_ : s_ - 1) & (kHand4 - 1));
+                const unsigned int tag = (unsigned int)(RIN == 1 ? s_ + 1 : s_);
+                LLW w;
+                s_peek_a(inA + slotIn * 512u, w);
+                if (!__all_sync(0xffffffffu, ok(w, tag))) {
+                    const long long c0 = clock64();
+                    while (!dead) {
+                        s_peek_a(inA + slotIn * 512u, w);
+                        if (__all_sync(0xffffffffu, ok(w, tag))) break;
+                        dead = spin_fail(c0);
+                    }
+                }
+                vkin = val(w);
+            }
+            // ---- j-face words of this warp's planes
+            double ve[W];
+#pragma unroll
+            for (int p = 0; p < W; p++) ve[p] = 0.0;
+            if (JI && s_ < jInEnd) {
+                const unsigned int hs = hjA + (unsigned int)(s_ & (kRing4 - 1)) * (MW * 16u), tag = (unsigned int)s_ + 1u;
+                LLW w[W];
+                bool good = true;
+#pragma unroll
+                for (int p = 0; p < W; p++) {
+                    s_peek_a(hs + p * 16u, w[p]);
+                    good = good && ok(w[p], tag);
+                }
+                if (!__all_sync(0xffffffffu, good)) {
+                    const long long c0 = clock64();
+                    while (!dead) {
+                        good = true;
+#pragma unroll
+                        for (int p = 0; p < W; p++) {
+                            s_peek_a(hs + p * 16u, w[p]);
+                            good = good && ok(w[p], tag);
+                        }
+                        if (__all_sync(0xffffffffu, good)) break;
+                        dead = spin_fail(c0);
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < W; p++) ve[p] = val(w[p]);
+            }
+            // ---- operands of this tick have landed
+            cp_async_wait<kD4 - 1>();
+            __syncwarp();
+            const double* o = ringP + slot * (kSlotBytes / 8);
+            double opk[W], opj[W], opi[W], src[W], vj[W], nr[W];
+#pragma unroll
+            for (int p = 0; p < W; p++) {
+                opk[p] = o[p * 32];
+                opj[p] = o[W * 32 + p * 32];
+                opi[p] = o[2 * W * 32 + p * 32];
+                src[p] = o[3 * W * 32 + p * 32];
+            }
+#pragma unroll
+            for (int p = 0; p < W; p++) {
+                vj[p] = BWD ? __shfl_down_sync(0xffffffffu, res[p], 1) : __shfl_up_sync(0xffffffffu, res[p], 1);
+                if (JI) vj[p] = (lane == edgeLane) ? ve[p] : vj[p];
+            }
+#pragma unroll
+            for (int p = 0; p < W; p++) {
+                const double vk = BWD ? (p < W - 1 ? res[p < W - 1 ? p + 1 : p] : vkin) : (p > 0 ? res[p > 0 ? p - 1 : p] : vkin);
+                double acc = __dsub_rn(src[p], __dmul_rn(opk[p], vk));
+                acc = __dsub_rn(acc, __dmul_rn(opj[p], vj[p]));
+                nr[p] = __dsub_rn(acc, __dmul_rn(opi[p], res[p]));
+            }
+#pragma unroll
+            for (int p = 0; p < W; p++) res[p] = nr[p];
+            // ---- hand-off to the next warp of the chain.  Its ring holds kHand4 ticks; every 4th tick make sure
+            // the consumer has freed the next four slots (the word of tick X is read by the consumer in ITS tick
+            // X+1: overwriting the slots of ticks s-kHand4 .. s-kHand4+3 needs the consumer to have completed tick s-kHand4+4)
+            if (ROUT == 1) {
+                if ((s_ & 3) == 0 && s_ >= kHand4 - 4 && __any_sync(0xffffffffu, sm->prog[q + 1] < s_ - (kHand4 - 5))) {
+                    const long long c0 = clock64();
+                    while (!dead) {     // warp votes keep the lanes together (volatile reads may differ per lane)
+                        if (__all_sync(0xffffffffu, sm->prog[q + 1] >= s_ - (kHand4 - 5))) break;
+                        dead = spin_fail(c0);
+                    }
+                }
+                const double v = BWD ? res[0] : res[W - 1];
+                const unsigned long long bb = (unsigned long long)__double_as_longlong(v);
+                s_store_a(outA + (unsigned int)(s_ & (kHand4 - 1)) * 512u, (unsigned int)bb, (unsigned int)(bb >> 32), (unsigned int)s_ + 1u);
+            } else if (ROUT == 2) {
+                if (s_ >= kOutLo && s_ < kOutHi) g_store(gKout + (long long)s_ * dSig * 32, BWD ? res[0] : res[W - 1], epoch);
+            }
+            if (JO) {
+                if (s_ >= jOutLo && s_ < jOutHi && lane == pubLane) {
+#pragma unroll
+                    for (int p = 0; p < W; p++) g_store(gJout + (long long)s_ * dSig * MW + p, res[p], epoch);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < W; p++)
+                if (s_ >= yLo[p] && s_ < yHi[p]) pY[p * 32] = res[p];
+            pY += tickStride;
+            // ---- refill this tick's ring slot, publish the progress
+            __syncwarp();
+            if (nIssued < ticks) { issue_next(slot); nIssued++; }
+            cp_async_commit();
+            slot = slot + 1u == (unsigned int)kD4 ? 0u : slot + 1u;
+            if (lane == 0) sm->prog[q] = s_ + 1;
+        }
+    };
+    {
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
+        using T = std::true_type;
+        using F = std::false_type;
+        const int rin = (q == 0) ? (kIn ? 1 : 0) : 2;
+        const int rout = !last ? 1 : (kOut ? 2 : 0);
+        auto byJ = [&](auto RIN_, auto ROUT_) {
+            if (jIn) { if (jOut) run(RIN_, ROUT_, T(), T()); else run(RIN_, ROUT_, T(), F()); }
+            else { if (jOut) run(RIN_, ROUT_, F(), T()); else run(RIN_, ROUT_, F(), F()); }
+        };
+        // q == 0 is never the last warp (M >= 2): 5 roles
+        if (rin == 0) byJ(I0(), I1());
+        else if (rin == 1) byJ(I1(), I1());
+        else if (rout == 1) byJ(I2(), I1());
+        else if (rout == 2) byJ(I2(), I2());
+        else byJ(I2(), I0());
+    }
+    cp_async_wait<0>();
+    if (dead && lane == 0) {
+        sm->abort = 1;
+        a.S->commError = 2;
+        a.S->done = 1;
+    }
+    if (trace && lane == 0) {
+        trace[2] = gtimer();
+        trace[7] = (unsigned long long)(clock64() - trStartC);
+    }
+    // the last warp of the chain of the last CTA re-arms the ticket for the next launch
+    if (last && lane == 0) {
+        __threadfence();
+        const unsigned int doneCtas = atomicAdd(&a.ticket[1], 1u);
+        if (doneCtas == (unsigned int)nCta - 1u) {
+            a.ticket[0] = 0u;
+            a.ticket[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // natural cell order <-> tile layout, 32 steps x 32 lines per CTA through shared memory
 // ---------------------------------------------------------------------------
@@ -1002,6 +1382,7 @@ struct ProductSlot {
 
 struct State2 {
     Box2 b;
+    int gen = 2, M4 = 0;
     int W = 16;
     long long padded = 0;
     double* Y = nullptr;
@@ -1047,13 +1428,25 @@ int pick_W(int nz)
     return nz >= 12 ? 6 : 4;
 }
 
-// 2 (default): plane-stacked CTAs (sweep2_kernel), 3: register-stacked warps (sweep3_kernel; measured on
-// B200, 216^3: 0.57 us per tick of one warp and 3-6 us per group-to-group hop = 590-610 us per sweep against
-// 450 us for sweep2_kernel -- correct and tested, not yet faster, hence opt-in)
+// 4 (default): chained register-stacked warps (sweep4_kernel); 2: plane-stacked CTAs (sweep2_kernel);
+// 3: one register-stacked warp per group (sweep3_kernel).  Measured on B200, us per sweep on 216^3 / 108^3:
+// generation 2: 449 / 183, generation 3: 590-610 / 260-290, generation 4 (8 warps x 2 planes): 371 / 174
 int box_generation()
 {
     const char* e = getenv("LDU_STENCIL");
-    return (e && atoi(e) == 3) ? 3 : 2;
+    const int v = e ? atoi(e) : 4;
+    return (v == 2 || v == 3) ? v : 4;
+}
+
+// chained warps (sweep4_kernel): warps per CTA; W = 2 planes per warp
+int pick_M4(int nz)
+{
+    const char* e = getenv("LDU_STENCIL_M");
+    if (e) {
+        const int m = atoi(e);
+        if (m == 2 || m == 4 || m == 8) return m;
+    }
+    return nz >= 32 ? 8 : nz >= 8 ? 4 : 2;
 }
 
 // planes per warp of the register-stacked sweeps: the chain of stack-to-stack hops costs
@@ -1081,8 +1474,11 @@ int state2(ldu_matrix* m, State2** out)
         b.nJ = (b.ny + 31) / 32;
         b.steps = b.nx + 31;
         b.nTiles = b.nz * b.nJ;
-        const bool v3 = box_generation() == 3;
-        s->W = v3 ? pick_W3(b.nz) : pick_W(b.nz);
+        const int gen = box_generation();
+        const bool v3 = gen >= 3;
+        s->gen = gen;
+        s->M4 = gen == 4 ? pick_M4(b.nz) : 0;
+        s->W = gen == 4 ? 2 * s->M4 : v3 ? pick_W3(b.nz) : pick_W(b.nz);
         b.nKg = (b.nz + s->W - 1) / s->W;
         b.W3 = v3 ? s->W : 0;
         b.ticks = b.steps + s->W - 1;
@@ -1194,6 +1590,55 @@ int launch_sweeps(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
     return LDU_OK;
 }
 
+template <int W, int M>
+int launch_sweeps4(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
+{
+    const size_t smem = sizeof(Smem4<W, M>);
+    if (!s->attrSet) {
+        LDU_CUDA(cudaFuncSetAttribute(sweep4_kernel<W, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LDU_CUDA(cudaFuncSetAttribute(sweep4_kernel<W, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s->attrSet = true;
+    }
+    const int grid = s->b.nKg * s->b.nJ;
+    cudaStream_t st = m->ctx->stream;
+    const char* tracePath = getenv("LDU_S2_TRACE");
+    const size_t nTrace = (size_t)grid * M * 8;
+    if (tracePath && !s->trace) LDU_CUDA(cudaMalloc((void**)&s->trace, nTrace * sizeof(unsigned long long)));
+    a.trace = tracePath ? s->trace : nullptr;
+    if (a.trace) LDU_CUDA(cudaMemsetAsync(a.trace, 0, nTrace * sizeof(unsigned long long), st));
+    a.dbg = getenv("LDU_S3_DBG") ? atoi(getenv("LDU_S3_DBG")) : 0;
+    const char* only = getenv("LDU_S3_ONLY");     // debug: "fwd" / "bwd" runs one of the two sweeps
+    a.epoch = ++s->epoch;
+    a.pk = P.F[0];
+    a.pj = P.F[1];
+    a.pi = P.F[2];
+    if (!(only && only[0] == 'b')) sweep4_kernel<W, M, false><<<grid, (M + 2) * 32, smem, st>>>(a);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    if (a.trace) {   // debug only: per-warp timeline of the forward sweep
+        // columns: ticket kg J q start_ns end_ns wordsCycles mathCycles operandWaitCycles handoffStoreCycles totalCycles
+        std::vector<unsigned long long> h(nTrace);
+        LDU_CUDA(cudaMemcpyAsync(h.data(), a.trace, nTrace * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        LDU_CUDA(cudaStreamSynchronize(st));
+        if (FILE* f = fopen(tracePath, "w")) {
+            for (size_t c = 0; c < (size_t)grid * M; c++)
+                fprintf(f, "%d %d %d %d %llu %llu %llu %llu %llu %llu %llu\n", (int)(c / M), (int)(h[8 * c] >> 40),
+                        (int)((h[8 * c] >> 20) & 0xfffff), (int)(h[8 * c] & 0xfffff), h[8 * c + 1], h[8 * c + 2],
+                        h[8 * c + 3], h[8 * c + 4], h[8 * c + 5], h[8 * c + 6], h[8 * c + 7]);
+            fclose(f);
+        }
+        a.trace = nullptr;
+    }
+    a.epoch = ++s->epoch;
+    a.pk = P.B[0];
+    a.pj = P.B[1];
+    a.pi = P.B[2];
+    if (!(only && only[0] == 'f')) sweep4_kernel<W, M, true><<<grid, (M + 2) * 32, smem, st>>>(a);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
 template <int W>
 int launch_sweeps3(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
 {
@@ -1247,10 +1692,10 @@ int launch_sweeps3(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
 int stencil_version(const ldu_matrix* m)
 {
     if (m->box[0] <= 0 || !flow_enabled()) return 0;
-    // 0: generic dataflow sweeps, 1: stencil.cu, 2 (default): stencil2.cu with plane-stacked CTAs,
-    // 3: stencil2.cu with register-stacked warps; 2 and 3 share every entry point
+    // 0: generic dataflow sweeps, 1: stencil.cu, 2 / 3 / 4 (default): the three kernel generations of
+    // stencil2.cu (box_generation), which share every entry point
     const char* e = getenv("LDU_STENCIL");
-    const int ver = e ? atoi(e) : 2;
+    const int ver = e ? atoi(e) : 4;
     return (ver < 0 || ver >= 2) ? 2 : ver;
 }
 
@@ -1307,7 +1752,10 @@ static int apply_core(ldu_matrix* m, const double* rD, const double* coefF, cons
     a.gK = s->gK;
     a.gJ = s->gJ;
     a.ticket = s->ticket;
-    if (s->b.W3 == 16) LDU_TRY(launch_sweeps3<16>(m, s, a, P));
+    if (s->gen == 4 && s->M4 == 8) LDU_TRY((launch_sweeps4<2, 8>(m, s, a, P)));
+    else if (s->gen == 4 && s->M4 == 4) LDU_TRY((launch_sweeps4<2, 4>(m, s, a, P)));
+    else if (s->gen == 4) LDU_TRY((launch_sweeps4<2, 2>(m, s, a, P)));
+    else if (s->b.W3 == 16) LDU_TRY(launch_sweeps3<16>(m, s, a, P));
     else if (s->b.W3 == 12) LDU_TRY(launch_sweeps3<12>(m, s, a, P));
     else if (s->b.W3 == 8) LDU_TRY(launch_sweeps3<8>(m, s, a, P));
     else if (s->b.W3 == 4) LDU_TRY(launch_sweeps3<4>(m, s, a, P));
