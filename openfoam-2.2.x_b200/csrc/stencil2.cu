@@ -890,53 +890,87 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
         constexpr int kPoll = 8;
         const bool forK = (warp == M);
         if (forK ? !kIn : !jIn) return;
-        const LLW* gIn = forK ? a.gK + ((long long)(BWD ? g + nJ : g - nJ) * steps) * 32 + lane
-                              : a.gJ + ((long long)(BWD ? g + 1 : g - 1) * nRho) * MW + (lane < MW ? lane : 0);
-        const unsigned int outA = forK ? (unsigned int)__cvta_generic_to_shared(&sm->kx[0][0][lane])
-                                       : (unsigned int)__cvta_generic_to_shared(&sm->hj[0][lane < MW ? lane : 0]);
-        const int rowWords = forK ? 32 : MW;
-        const unsigned int slotBytes = (unsigned int)rowWords * 16u;
-        const int ringMask = forK ? kHand4 - 1 : kRing4 - 1;
-        const bool mine = lane < rowWords;
-        int sn = 0;                                          // next loop tick to forward
-        long long tstart = 0;
-        for (int spin = 0; sn < ticks;) {
-            if (sm->abort) break;
-            int cap;
-            if (forK) {
-                cap = min(ticks, sm->prog[0] + kHand4 - 1);
-            } else {
-                int minProg = sm->prog[0];
+        if (forK) {
+            // ---- k-face rows: all 32 words of a row are published by one warp in one instruction
+            const LLW* gIn = a.gK + ((long long)(BWD ? g + nJ : g - nJ) * steps) * 32 + lane;
+            const unsigned int outA = (unsigned int)__cvta_generic_to_shared(&sm->kx[0][0][lane]);
+            int sn = 0;                                          // next loop tick to forward
+            long long tstart = 0;
+            for (int spin = 0; sn < ticks;) {
+                if (sm->abort) break;
+                const int cap = min(ticks, sm->prog[0] + kHand4 - 1);
+                while (sn < cap && k_row(sn) < 0) sn++;
+                LLW w[kPoll];
+                int r[kPoll];
 #pragma unroll
-                for (int w_ = 1; w_ < M; w_++) minProg = min(minProg, sm->prog[w_]);
-                cap = min(ticks, minProg + kRing4 - 1);
-            }
-            while (sn < cap && (forK ? k_row(sn) : j_row(sn)) < 0) sn++;
-            LLW w[kPoll];
-            int r[kPoll];
+                for (int i = 0; i < kPoll; i++) {
+                    r[i] = (sn + i < cap) ? k_row(sn + i) : -1;
+                    if (r[i] >= 0) g_peek(gIn + (long long)r[i] * 32, w[i]);
+                }
+                bool did = false;
 #pragma unroll
-            for (int i = 0; i < kPoll; i++) {
-                r[i] = (sn + i < cap) ? (forK ? k_row(sn + i) : j_row(sn + i)) : -1;
-                if (r[i] >= 0 && mine) g_peek(gIn + (long long)r[i] * rowWords, w[i]);
+                for (int i = 0; i < kPoll; i++) {       // rows become valid in order
+                    if (r[i] < 0 || !__all_sync(0xffffffffu, ok(w[i], epoch))) break;
+                    s_store_a(outA + (unsigned int)(sn & (kHand4 - 1)) * 512u, w[i].lo, w[i].hi, (unsigned int)sn + 1u);
+                    sn++;
+                    did = true;
+                }
+                if (did) {
+                    spin = 0;
+                    tstart = 0;
+                } else if ((++spin & 63) == 63) {
+                    if (tstart == 0) tstart = clock64();
+                    else if (clock64() - tstart > kTimeout2) {
+                        sm->abort = 1;
+                        a.S->commError = 2;
+                        a.S->done = 1;
+                        break;
+                    }
+                }
             }
-            bool did = false;
+            return;
+        }
+        // ---- j-face words: lane p forwards the words of plane p on its own.  The warps of the producing chain
+        // publish their words of a row at different times (warp q runs q ticks behind warp 0) and the warps of
+        // this chain need them at different times: a row-wise hand-over would make warp 0 wait for warp M-1
+        {
+            const int p = lane < MW ? lane : 0;
+            const bool mine = lane < MW;
+            const LLW* gIn = a.gJ + ((long long)(BWD ? g + 1 : g - 1) * nRho) * MW + p;
+            const unsigned int outA = (unsigned int)__cvta_generic_to_shared(&sm->hj[0][p]);
+            const int qOfPlane = BWD ? M - 1 - p / W : p / W;       // chain position of the warp that consumes plane p
+            int sn = mine ? 0 : ticks;
+            long long tstart = 0;
+            for (int spin = 0;;) {
+                if (__all_sync(0xffffffffu, sn >= ticks) || sm->abort) break;
+                const int cap = min(ticks, sm->prog[qOfPlane] + kRing4 - 1);
+                while (sn < cap && j_row(sn) < 0) sn++;
+                LLW w[kPoll];
+                int r[kPoll];
 #pragma unroll
-            for (int i = 0; i < kPoll; i++) {       // rows become valid in order
-                if (r[i] < 0 || !__all_sync(0xffffffffu, !mine || ok(w[i], epoch))) break;
-                if (mine) s_store_a(outA + (unsigned int)(sn & ringMask) * slotBytes, w[i].lo, w[i].hi, (unsigned int)sn + 1u);
-                sn++;
-                did = true;
-            }
-            if (did) {
-                spin = 0;
-                tstart = 0;
-            } else if ((++spin & 63) == 63) {
-                if (tstart == 0) tstart = clock64();
-                else if (clock64() - tstart > kTimeout2) {
-                    sm->abort = 1;
-                    a.S->commError = 2;
-                    a.S->done = 1;
-                    break;
+                for (int i = 0; i < kPoll; i++) {
+                    r[i] = (sn + i < cap) ? j_row(sn + i) : -1;
+                    if (r[i] >= 0) g_peek(gIn + (long long)r[i] * MW, w[i]);
+                }
+                bool did = false;
+#pragma unroll
+                for (int i = 0; i < kPoll; i++) {       // the words of a plane become valid in order
+                    if (r[i] < 0 || !ok(w[i], epoch)) break;
+                    s_store_a(outA + (unsigned int)(sn & (kRing4 - 1)) * (MW * 16u), w[i].lo, w[i].hi, (unsigned int)sn + 1u);
+                    sn++;
+                    did = true;
+                }
+                if (__any_sync(0xffffffffu, did)) {
+                    spin = 0;
+                    tstart = 0;
+                } else if ((++spin & 63) == 63) {
+                    if (tstart == 0) tstart = clock64();
+                    else if (clock64() - tstart > kTimeout2) {
+                        sm->abort = 1;
+                        a.S->commError = 2;
+                        a.S->done = 1;
+                        break;
+                    }
                 }
             }
         }
@@ -1033,15 +1067,16 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
     // (measured: the loop with everything but its control flow removed cost 500 of 820 cycles per tick).
     //   RIN  0: no k input, 1: from the helper (stack below), 2: from warp q-1
     //   ROUT 0: nothing, 1: hand-off to warp q+1, 2: the stack's k-face to L2
-    auto run = [&](auto RIN_, auto ROUT_, auto JI_, auto JO_) {
+    //   STEADY: the middle segment of the loop, where every range test below is true
+    unsigned int slot = 0;
+    auto run = [&](auto RIN_, auto ROUT_, auto JI_, auto JO_, auto STEADY_, int sBegin, int sEnd) {
         constexpr int RIN = decltype(RIN_)::value, ROUT = decltype(ROUT_)::value;
-        constexpr bool JI = decltype(JI_)::value, JO = decltype(JO_)::value;
-        unsigned int slot = 0;
+        constexpr bool JI = decltype(JI_)::value, JO = decltype(JO_)::value, STEADY = decltype(STEADY_)::value;
 #pragma unroll 1
-        for (int s_ = 0; s_ < ticks; s_++) {
+        for (int s_ = sBegin; s_ < sEnd; s_++) {
             // ---- k input: from the helper (row of this tick, tag s+1) or from warp q-1 (its tick s-1, tag s)
             double vkin = 0.0;
-            if (RIN == 1 ? (s_ < kInEnd) : (RIN == 2 && s_ > 0)) {
+            if (RIN == 1 ? (STEADY || s_ < kInEnd) : (RIN == 2 && (STEADY || s_ > 0))) {
                 const unsigned int slotIn = (unsigned int)((RIN == 1 ? s_ : s_ - 1) & (kHand4 - 1));
                 const unsigned int tag = (unsigned int)(RIN == 1 ? s_ + 1 : s_);
                 LLW w;
@@ -1060,7 +1095,7 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
             double ve[W];
 #pragma unroll
             for (int p = 0; p < W; p++) ve[p] = 0.0;
-            if (JI && s_ < jInEnd) {
+            if (JI && (STEADY || s_ < jInEnd)) {
                 const unsigned int hs = hjA + (unsigned int)(s_ & (kRing4 - 1)) * (MW * 16u), tag = (unsigned int)s_ + 1u;
                 LLW w[W];
                 bool good = true;
@@ -1126,21 +1161,21 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
                 const unsigned long long bb = (unsigned long long)__double_as_longlong(v);
                 s_store_a(outA + (unsigned int)(s_ & (kHand4 - 1)) * 512u, (unsigned int)bb, (unsigned int)(bb >> 32), (unsigned int)s_ + 1u);
             } else if (ROUT == 2) {
-                if (s_ >= kOutLo && s_ < kOutHi) g_store(gKout + (long long)s_ * dSig * 32, BWD ? res[0] : res[W - 1], epoch);
+                if (STEADY || (s_ >= kOutLo && s_ < kOutHi)) g_store(gKout + (long long)s_ * dSig * 32, BWD ? res[0] : res[W - 1], epoch);
             }
             if (JO) {
-                if (s_ >= jOutLo && s_ < jOutHi && lane == pubLane) {
+                if ((STEADY || (s_ >= jOutLo && s_ < jOutHi)) && lane == pubLane) {
 #pragma unroll
                     for (int p = 0; p < W; p++) g_store(gJout + (long long)s_ * dSig * MW + p, res[p], epoch);
                 }
             }
 #pragma unroll
             for (int p = 0; p < W; p++)
-                if (s_ >= yLo[p] && s_ < yHi[p]) pY[p * 32] = res[p];
+                if (STEADY || (s_ >= yLo[p] && s_ < yHi[p])) pY[p * 32] = res[p];
             pY += tickStride;
             // ---- refill this tick's ring slot, publish the progress
             __syncwarp();
-            if (nIssued < ticks) { issue_next(slot); nIssued++; }
+            if (STEADY || nIssued < ticks) { issue_next(slot); nIssued++; }
             cp_async_commit();
             slot = slot + 1u == (unsigned int)kD4 ? 0u : slot + 1u;
             if (lane == 0) sm->prog[q] = s_ + 1;
@@ -1154,9 +1189,27 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
         using F = std::false_type;
         const int rin = (q == 0) ? (kIn ? 1 : 0) : 2;
         const int rout = !last ? 1 : (kOut ? 2 : 0);
+        // the steady segment: all planes of the warp inside their step range, all faces inside their row ranges,
+        // the prefetch never past the end
+        int sLo = 1, sHi = ticks - kD4;
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            sLo = max(sLo, yLo[p]);
+            sHi = min(sHi, yHi[p]);
+        }
+        if (rin == 1) sHi = min(sHi, kInEnd);
+        if (jIn) sHi = min(sHi, jInEnd);
+        if (rout == 2) { sLo = max(sLo, kOutLo); sHi = min(sHi, kOutHi); }
+        if (jOut) { sLo = max(sLo, jOutLo); sHi = min(sHi, jOutHi); }
+        if (sHi < sLo) sHi = sLo;
+        auto three = [&](auto RIN_, auto ROUT_, auto JI_, auto JO_) {
+            run(RIN_, ROUT_, JI_, JO_, F(), 0, sLo);
+            run(RIN_, ROUT_, JI_, JO_, T(), sLo, sHi);
+            run(RIN_, ROUT_, JI_, JO_, F(), sHi, ticks);
+        };
         auto byJ = [&](auto RIN_, auto ROUT_) {
-            if (jIn) { if (jOut) run(RIN_, ROUT_, T(), T()); else run(RIN_, ROUT_, T(), F()); }
-            else { if (jOut) run(RIN_, ROUT_, F(), T()); else run(RIN_, ROUT_, F(), F()); }
+            if (jIn) { if (jOut) three(RIN_, ROUT_, T(), T()); else three(RIN_, ROUT_, T(), F()); }
+            else { if (jOut) three(RIN_, ROUT_, F(), T()); else three(RIN_, ROUT_, F(), F()); }
         };
         // q == 0 is never the last warp (M >= 2): 5 roles
         if (rin == 0) byJ(I0(), I1());
