@@ -1068,7 +1068,28 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
     //   RIN  0: no k input, 1: from the helper (stack below), 2: from warp q-1
     //   ROUT 0: nothing, 1: hand-off to warp q+1, 2: the stack's k-face to L2
     //   STEADY: the middle segment of the loop, where every range test below is true
+    // The operands of a tick are read from the ring at the END of the previous tick (software pipelining: their LDS
+    // latency hides behind the next tick's face-word poll, and nothing but the poll stands between the start of a
+    // tick and its hand-off): cur* hold the operands of the coming tick, `slot` is the ring slot they came from + 1
+    double opk[W], opj[W], opi[W], src[W];
     unsigned int slot = 0;
+    auto load_operands = [&]() {      // ring slot `slot` -> registers; refill it with tick `nIssued`; advance
+        cp_async_wait<kD4 - 1>();
+        __syncwarp();
+        const double* o = ringP + slot * (kSlotBytes / 8);
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            opk[p] = o[p * 32];
+            opj[p] = o[W * 32 + p * 32];
+            opi[p] = o[2 * W * 32 + p * 32];
+            src[p] = o[3 * W * 32 + p * 32];
+        }
+        __syncwarp();
+    };
+    load_operands();
+    if (nIssued < ticks) { issue_next(slot); nIssued++; }
+    cp_async_commit();
+    slot = slot + 1u == (unsigned int)kD4 ? 0u : slot + 1u;
     auto run = [&](auto RIN_, auto ROUT_, auto JI_, auto JO_, auto STEADY_, int sBegin, int sEnd) {
         constexpr int RIN = decltype(RIN_)::value, ROUT = decltype(ROUT_)::value;
         constexpr bool JI = decltype(JI_)::value, JO = decltype(JO_)::value, STEADY = decltype(STEADY_)::value;
@@ -1120,18 +1141,7 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
 #pragma unroll
                 for (int p = 0; p < W; p++) ve[p] = val(w[p]);
             }
-            // ---- operands of this tick have landed
-            cp_async_wait<kD4 - 1>();
-            __syncwarp();
-            const double* o = ringP + slot * (kSlotBytes / 8);
-            double opk[W], opj[W], opi[W], src[W], vj[W], nr[W];
-#pragma unroll
-            for (int p = 0; p < W; p++) {
-                opk[p] = o[p * 32];
-                opj[p] = o[W * 32 + p * 32];
-                opi[p] = o[2 * W * 32 + p * 32];
-                src[p] = o[3 * W * 32 + p * 32];
-            }
+            double vj[W], nr[W];
 #pragma unroll
             for (int p = 0; p < W; p++) {
                 vj[p] = BWD ? __shfl_down_sync(0xffffffffu, res[p], 1) : __shfl_up_sync(0xffffffffu, res[p], 1);
@@ -1173,12 +1183,12 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
             for (int p = 0; p < W; p++)
                 if (STEADY || (s_ >= yLo[p] && s_ < yHi[p])) pY[p * 32] = res[p];
             pY += tickStride;
-            // ---- refill this tick's ring slot, publish the progress
-            __syncwarp();
+            if (lane == 0) sm->prog[q] = s_ + 1;
+            // ---- operands of the next tick into registers, its ring slot refilled
+            if (STEADY || s_ + 1 < ticks) load_operands();
             if (STEADY || nIssued < ticks) { issue_next(slot); nIssued++; }
             cp_async_commit();
             slot = slot + 1u == (unsigned int)kD4 ? 0u : slot + 1u;
-            if (lane == 0) sm->prog[q] = s_ + 1;
         }
     };
     {
@@ -1191,7 +1201,7 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
         const int rout = !last ? 1 : (kOut ? 2 : 0);
         // the steady segment: all planes of the warp inside their step range, all faces inside their row ranges,
         // the prefetch never past the end
-        int sLo = 1, sHi = ticks - kD4;
+        int sLo = 1, sHi = ticks - kD4 - 1;
 #pragma unroll
         for (int p = 0; p < W; p++) {
             sLo = max(sLo, yLo[p]);
