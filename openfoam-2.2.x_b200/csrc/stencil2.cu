@@ -52,6 +52,9 @@
 //       hops 13 instead of 17-25 us, stack hops 5.5 instead of 3.7 us: no net gain)
 // A tick still costs ~470 cycles (60-70 dependent instructions per step and plane); the
 // barrier + hand-off chain alone is 105.
+// Round 2 added two more generations below (sweep3_kernel: one register-stacked warp per group, 590-610 us;
+// sweep4_kernel: chains of eight such warps per CTA, 344 us -- the default); their headers and DESIGN.md 4
+// have the measurements.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
