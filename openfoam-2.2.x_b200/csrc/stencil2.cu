@@ -1036,6 +1036,8 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
         trace[1] = gtimer();
     }
     bool dead = false;
+    unsigned int spins = 0;                  // the time-out / abort test runs every 256th poll: a spinning warp shares
+                                             // its sub-partition's issue slots with a working one
     auto spin_fail = [&](long long c0) {     // warp-uniform time-out / abort test of a spin loop
         bool bad = sm->abort != 0 || clock64() - c0 > kTimeout2;
         return __any_sync(0xffffffffu, bad);
@@ -1110,7 +1112,7 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
                     while (!dead) {
                         s_peek_a(inA + slotIn * 512u, w);
                         if (__all_sync(0xffffffffu, ok(w, tag))) break;
-                        dead = spin_fail(c0);
+                        if ((++spins & 255u) == 0u) dead = spin_fail(c0);
                     }
                 }
                 vkin = val(w);
@@ -1138,7 +1140,7 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
                             good = good && ok(w[p], tag);
                         }
                         if (__all_sync(0xffffffffu, good)) break;
-                        dead = spin_fail(c0);
+                        if ((++spins & 255u) == 0u) dead = spin_fail(c0);
                     }
                 }
 #pragma unroll
@@ -1167,7 +1169,7 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
                     const long long c0 = clock64();
                     while (!dead) {     // warp votes keep the lanes together (volatile reads may differ per lane)
                         if (__all_sync(0xffffffffu, sm->prog[q + 1] >= s_ - (kHand4 - 5))) break;
-                        dead = spin_fail(c0);
+                        if ((++spins & 255u) == 0u) dead = spin_fail(c0);
                     }
                 }
                 const double v = BWD ? res[0] : res[W - 1];
