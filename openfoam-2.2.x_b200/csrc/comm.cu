@@ -149,6 +149,15 @@ static int halo_grid(ldu_matrix* m, dim3& grid, IfaceDev** tab)
         set_error("exchange window too small for this matrix's interfaces");
         return LDU_ECOMM;
     }
+    // a wrong neighbour rank / interface index would be an out-of-bounds store into a peer's HBM
+    for (const Interface& it : m->ifs) {
+        if (it.nbrRank < 0 || it.nbrRank >= ctx->comm.nRanks || it.nbrInterface < 0
+            || it.nbrInterface >= ctx->comm.maxInterfaces) {
+            set_error("interface names a neighbour rank / interface outside the exchange window "
+                      "(nbrRank < nRanks and nbrInterface < maxInterfaces of ldu_comm_window_create)");
+            return LDU_EINVAL;
+        }
+    }
     LDU_TRY(ensure_iface_table(m, tab));
     grid = dim3(std::max(1, std::min(16, (maxN + kBlock - 1) / kBlock)), (unsigned)m->ifs.size());
     return LDU_OK;

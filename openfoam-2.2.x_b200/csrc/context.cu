@@ -40,7 +40,7 @@ static int upload(ldu_context* ctx, T** d, const T* h, size_t n, size_t pad = 0)
 // large copies from / to pageable host memory: several host threads stage chunks through pinned buffers
 // ---------------------------------------------------------------------------
 namespace {
-constexpr int kStageThreads = 6;
+constexpr int kStageThreads = 12;    // upper bound; LDU_STAGE_THREADS picks fewer (default 8)
 constexpr size_t kStageChunk = 4u << 20;
 constexpr size_t kStageMin = 1u << 20;     // below this a plain copy is as fast
 
@@ -87,7 +87,14 @@ int staged_copy(ldu_context* ctx, unsigned char* dst, const unsigned char* src, 
     LDU_TRY(stage_pool(ctx, &sp));
     LDU_CUDA(cudaStreamSynchronize(ctx->stream));     // ordered after what is queued on the context's stream
     const size_t nChunks = (bytes + kStageChunk - 1) / kStageChunk;
-    const int nThreads = (int)std::min<size_t>(kStageThreads, nChunks);
+    static const int wanted = [] {
+        const char* e = getenv("LDU_STAGE_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        int n = e ? atoi(e) : 8;
+        if (hw > 0) n = std::min(n, std::max(hw - 1, 1));
+        return std::max(1, std::min(n, kStageThreads));
+    }();
+    const int nThreads = (int)std::min<size_t>((size_t)wanted, nChunks);
     std::vector<cudaError_t> err(nThreads, cudaSuccess);
     auto work = [&](int t) {
         cudaSetDevice(ctx->device);
