@@ -52,7 +52,7 @@ def main():
     results["gs"] = bool(np.array_equal(psi, sm))
     # every smoother with interface updates (nonBlockingGaussSeidel consumes the halo after the
     # cells below the first coupled cell: another rounding order on the coupled rows)
-    for name in ("symGaussSeidel", "nonBlockingGaussSeidel", "DIC", "FDIC", "DICGaussSeidel"):
+    for name in ("symGaussSeidel", "nonBlockingGaussSeidel", "DIC", "FDIC", "DICGaussSeidel", "multiColourGaussSeidel"):
         sm = w.smooth(name, xs, [r["source"] for r in regs], 3)[rank]
         psi = xs[rank].copy()
         ldub200.lduMatrix.smoother.New("p", A, name).smooth(psi, reg["source"], 3)
@@ -64,6 +64,13 @@ def main():
     psi = reg["psi0"].copy()
     perf = ldub200.lduMatrix.solver.New("p", A, dict(ctl, referenceOrderSums=True)).solve(psi, reg["source"])
     results["gamg_nbgs"] = bool(perf.nIterations == perf_o["nIterations"] and np.array_equal(psi, psi_o[rank]))
+    # GAMG with the multi-colour smoother on every level of every region
+    ctl = dict(solver="GAMG", smoother="multiColourGaussSeidel", agglomerator="faceAreaPair",
+               nCellsInCoarsestLevel=4, mergeLevels=1, tolerance=1e-8, relTol=0)
+    psi_o, perf_o = w.solve(ctl, [r["psi0"] for r in regs], [r["source"] for r in regs])
+    psi = reg["psi0"].copy()
+    perf = ldub200.lduMatrix.solver.New("p", A, dict(ctl, referenceOrderSums=True)).solve(psi, reg["source"])
+    results["gamg_mcgs"] = bool(perf.nIterations == perf_o["nIterations"] and np.array_equal(psi, psi_o[rank]))
     solves = [dict(solver="PCG", preconditioner="DIC", tolerance=1e-8, relTol=0),
               dict(solver="PCG", preconditioner="diagonal", tolerance=1e-7, relTol=0),
               dict(solver="GAMG", smoother="GaussSeidel", agglomerator="faceAreaPair", nCellsInCoarsestLevel=4,

@@ -44,9 +44,10 @@ def _run(world, n=12, timeout=600):
 def test_multi_region_parity(world):
     for rank, r in enumerate(_run(world)):
         assert r["amul"] and r["residual"] and r["sumA"] and r["gs"], (rank, r)
-        for name in ("symGaussSeidel", "nonBlockingGaussSeidel", "DIC", "FDIC", "DICGaussSeidel"):
+        for name in ("symGaussSeidel", "nonBlockingGaussSeidel", "DIC", "FDIC", "DICGaussSeidel",
+                     "multiColourGaussSeidel"):
             assert r["smooth_" + name], (rank, name, r)
-        assert r["gamg_nbgs"], (rank, r)
+        assert r["gamg_nbgs"] and r["gamg_mcgs"], (rank, r)
         for i in range(3):
             it, ito = r[f"solve{i}_exact_iters"]
             assert it == ito, (rank, i, r)
