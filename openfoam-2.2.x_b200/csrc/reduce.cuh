@@ -81,12 +81,14 @@ __device__ __forceinline__ void reduce_tail(double (&acc)[NRED], const ReduceCtx
             tot[k] = __dadd_rn(tot[k], __ldcg(&rc.partials[(size_t)b * NRED + k]));
     }
     block_sum<NRED>(tot, smem);
-    if (threadIdx.x == 0) {
-        *rc.ticket = 0u;  // re-arm for the next launch on this stream
-        if (rc.comm.nRanks > 1) comm_allreduce_dev<NRED>(rc.comm, tot, rc.S);
+    if (threadIdx.x < 32) {      // the first warp, converged (block_sum ends with a barrier); totals valid in lane 0
+        if (threadIdx.x == 0) *rc.ticket = 0u;  // re-arm for the next launch on this stream
+        if (rc.comm.nRanks > 1) comm_allreduce_warp<NRED>(rc.comm, tot, rc.S);
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < NRED; k++) rc.red[k] = tot[k];
-        epi(rc.S, tot);
+            for (int k = 0; k < NRED; k++) rc.red[k] = tot[k];
+            epi(rc.S, tot);
+        }
     }
 }
 
