@@ -827,13 +827,14 @@ __global__ void __launch_bounds__(64, 1) sweep3_kernel(S2Args a)
 // arithmetic are those of sweep3_kernel with W3 = M*W planes per stack.
 // ---------------------------------------------------------------------------
 constexpr int kRing4 = 16;     // ticks of forwarded j-face words
-constexpr int kHand4 = 16;     // ticks of warp-to-warp hand-off words (also the ring of the stack's k-face words)
+// ticks of warp-to-warp hand-off words (also the ring of the stack's k-face words): 16, 8 for chains of 16 warps
+template <int M> struct Hand4 { static constexpr int value = M > 8 ? 8 : 16; };
 constexpr int kD4 = 8;         // operand ring depth (ticks) of every warp
 
 template <int W, int M>
 struct Smem4 {
     double ops[M][kD4][4][W][32];   // operand rings
-    LLW kx[M][kHand4][32];          // kx[q]: input words of pipeline warp q (q = 0: from the helper)
+    LLW kx[M][Hand4<M>::value][32];          // kx[q]: input words of pipeline warp q (q = 0: from the helper)
     LLW hj[kRing4][M * W];          // helper -> all warps: j-face row of loop tick s in slot s % kRing4, tag s + 1
     volatile int prog[M];           // ticks completed by pipeline warp q
     volatile int abort;
@@ -844,6 +845,7 @@ template <int W, int M, bool BWD>
 __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
 {
     constexpr int MW = M * W;
+    constexpr int kHand4 = Hand4<M>::value;
     extern __shared__ uint4 smem_raw[];
     Smem4<W, M>* sm = reinterpret_cast<Smem4<W, M>*>(smem_raw);
     if (a.guarded && a.S->done) return;
@@ -1044,6 +1046,14 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
     };
     auto issue_next = [&](unsigned int slot) {
         const unsigned int d = ring + slot * kSlotBytes;
+        if (W == 1) {      // a row is 256 B: 16 lanes x 16 B
+            if (lane < 16) {
+                cp_async16(d, nPk);
+                cp_async16(d + kOpBytes, nPj);
+                cp_async16(d + 2u * kOpBytes, nPi);
+                cp_async16(d + 3u * kOpBytes, nY);
+            }
+        }
 #pragma unroll
         for (int c = 0; c < W / 2; c++) {
             cp_async16(d + c * 512u, nPk + c * 64);
@@ -1512,7 +1522,7 @@ int pick_M4(int nz)
     const char* e = getenv("LDU_STENCIL_M");
     if (e) {
         const int m = atoi(e);
-        if (m == 2 || m == 4 || m == 8) return m;
+        if (m == 2 || m == 4 || m == 8 || m == 16) return m;    // 16: chains of 16 warps with ONE plane each
     }
     return nz >= 32 ? 8 : nz >= 8 ? 4 : 2;
 }
@@ -1546,7 +1556,7 @@ int state2(ldu_matrix* m, State2** out)
         const bool v3 = gen >= 3;
         s->gen = gen;
         s->M4 = gen == 4 ? pick_M4(b.nz) : 0;
-        s->W = gen == 4 ? 2 * s->M4 : v3 ? pick_W3(b.nz) : pick_W(b.nz);
+        s->W = gen == 4 ? (s->M4 == 16 ? 16 : 2 * s->M4) : v3 ? pick_W3(b.nz) : pick_W(b.nz);
         b.nKg = (b.nz + s->W - 1) / s->W;
         b.W3 = v3 ? s->W : 0;
         b.ticks = b.steps + s->W - 1;
@@ -1820,7 +1830,8 @@ static int apply_core(ldu_matrix* m, const double* rD, const double* coefF, cons
     a.gK = s->gK;
     a.gJ = s->gJ;
     a.ticket = s->ticket;
-    if (s->gen == 4 && s->M4 == 8) LDU_TRY((launch_sweeps4<2, 8>(m, s, a, P)));
+    if (s->gen == 4 && s->M4 == 16) LDU_TRY((launch_sweeps4<1, 16>(m, s, a, P)));
+    else if (s->gen == 4 && s->M4 == 8) LDU_TRY((launch_sweeps4<2, 8>(m, s, a, P)));
     else if (s->gen == 4 && s->M4 == 4) LDU_TRY((launch_sweeps4<2, 4>(m, s, a, P)));
     else if (s->gen == 4) LDU_TRY((launch_sweeps4<2, 2>(m, s, a, P)));
     else if (s->b.W3 == 16) LDU_TRY(launch_sweeps3<16>(m, s, a, P));
