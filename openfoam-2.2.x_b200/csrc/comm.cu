@@ -235,6 +235,12 @@ int ldu_comm_window_create(ldu_context* ctx, int rank, int nRanks, int maxInterf
     Comm& cm = ctx->comm;
     if (cm.window) {   // a window the library made for cyclic-only matrices, or an earlier call: replace it
         LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (cm.connected)      // the peers' windows mapped by the earlier ldu_comm_connect
+            for (int r = 0; r < cm.nRanks; r++)
+                if (r != cm.rank && cm.peer[r]) {
+                    cudaIpcCloseMemHandle(cm.peer[r]);
+                    cm.peer[r] = nullptr;
+                }
         cudaFree(cm.window);
         cudaFree(cm.d_peer);
         cm.window = nullptr;

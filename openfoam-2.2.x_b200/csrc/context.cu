@@ -512,6 +512,11 @@ int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lower
     }
     ldu_matrix* m = new ldu_matrix();
     m->ctx = ctx;
+    // any failure below releases what has been built so far (ldu_matrix_destroy copes with a half-built matrix)
+    struct Guard {
+        ldu_matrix* m;
+        ~Guard() { if (m) ldu_matrix_destroy(m); }
+    } guard{m};
     m->nCells = nCells;
     m->nFaces = nFaces;
     m->h_l.assign(lowerAddr, lowerAddr + nFaces);
@@ -577,7 +582,6 @@ int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lower
             const int c = faceCells[i][k];
             if (c < 0 || c >= nCells) {
                 set_error("ldu_matrix_create: interface faceCells out of range");
-                delete m;
                 return LDU_EINVAL;
             }
             cells.push_back(c);
@@ -611,6 +615,7 @@ int ldu_matrix_create(ldu_context* ctx, int nCells, int nFaces, const int* lower
     }
     LDU_TRY(ensure_scalars(m));
     LDU_CUDA(cudaStreamSynchronize(ctx->stream));
+    guard.m = nullptr;
     *out = m;
     return LDU_OK;
 }
