@@ -963,17 +963,64 @@ int gamg_solve(ldu_matrix* m, const ldu_controls* c, double* psi, const double* 
     // the flag must be clear while the V-cycle's unguarded and guarded kernels run
     VcycleState vs;
     LDU_TRY(vcycle_init(m, c, vs));
+    auto one_cycle = [&]() -> int {
+        LDU_TRY(vcycle(m, c, vs, psi, source, Apsi, finestCorrection, finestResidual, false));
+        LDU_TRY(k_amul(m, Apsi, psi, false));
+        return launch_map_reduce<1, false>(m, n, ResidualFromMap{finestResidual, source, Apsi}, EpiResidual<false>{1});
+    };
+    // A V-cycle is a couple of hundred launches, most of them on levels so small that the kernel is shorter than
+    // the launch call: from the second cycle on the whole cycle (V-cycle + residual) is replayed as ONE CUDA graph.
+    // The first cycle runs eagerly (it allocates the lazily created work fields, schedules and colourings, which
+    // a capture must not do).  Single-region solves whose coarsest level is solved by the one-kernel solver only
+    // (the coupled coarsest solver polls the host); anything the capture refuses falls back to eager launches.
+    const char* graphEnv = getenv("LDU_GAMG_GRAPH");
+    GamgLevel* Lc = m->levels.back();
+    // ... and only with the multi-colour smoother: the lexicographic sweeps (dataflow and box kernels) tag their
+    // words with an epoch the HOST increments per launch, which a replayed graph would freeze
+    bool useGraph = !(graphEnv && graphEnv[0] == '0') && m->ctx->comm.nRanks == 1 && m->nIfFaces == 0
+                    && c->smoother == LDU_SMOOTHER_MCGS && Lc->coarse->nCells <= 8192
+                    && !getenv("LDU_GAMG_GENERIC_COARSEST");
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t st = m->ctx->stream;
     int rc = LDU_OK;
-    for (;;) {
-        rc = vcycle(m, c, vs, psi, source, Apsi, finestCorrection, finestResidual, false);
-        if (rc != LDU_OK) break;
-        rc = k_amul(m, Apsi, psi, false);
-        if (rc != LDU_OK) break;
-        rc = launch_map_reduce<1, false>(m, n, ResidualFromMap{finestResidual, source, Apsi}, EpiResidual<false>{1});
+    for (int cycle = 0;; cycle++) {
+        if (useGraph && cycle >= 1) {
+            if (!exec) {
+                cudaGraph_t graph = nullptr;
+                const long long launchesBefore = g_launches;
+                bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    const int crc = one_cycle();
+                    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+                    ok = crc == LDU_OK && e == cudaSuccess && graph != nullptr;
+                    m->graphLaunches = (int)(g_launches - launchesBefore);
+                    g_launches = launchesBefore;        // nothing has run yet
+                }
+                if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                if (!ok) {
+                    cudaGetLastError();
+                    exec = nullptr;
+                    useGraph = false;
+                }
+            }
+            if (exec) {
+                if (cudaGraphLaunch(exec, st) != cudaSuccess) {
+                    rc = cuda_fail(cudaGetLastError(), "cudaGraphLaunch", __FILE__, __LINE__);
+                    break;
+                }
+                g_launches += m->graphLaunches;
+                rc = read_scalars(m, &hs);
+                if (rc != LDU_OK || hs.done) break;
+                continue;
+            }
+        }
+        rc = one_cycle();
         if (rc != LDU_OK) break;
         rc = read_scalars(m, &hs);
         if (rc != LDU_OK || hs.done) break;
     }
+    if (exec) cudaGraphExecDestroy(exec);
     vcycle_release(vs);
     return rc;
 }

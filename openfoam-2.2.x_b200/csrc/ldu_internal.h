@@ -214,6 +214,7 @@ struct ldu_matrix {
     bool precondHierarchyReady = false;   // GAMG-as-preconditioner: coarse coefficients current
     ldu_controls hierarchyControls;
     bool isCoarse = false;
+    int graphLaunches = 0;             // kernels in one captured GAMG cycle (launch accounting)
     bool referenceOrderSums = false;   // reductions accumulate in the reference's loop order
 };
 
