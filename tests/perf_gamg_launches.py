@@ -19,6 +19,6 @@ A.set_face_weights(s["faceWeights"])
 d_psi = ldub200.DeviceField(ctx, s["nCells"])
 d_src = ldub200.DeviceField(ctx, s["nCells"], s["source"])
 ctl = dict(solver="GAMG", smoother=smoother, agglomerator="faceAreaPair", nCellsInCoarsestLevel=10, mergeLevels=1,
-           cacheAgglomeration=True, nPreSweeps=0, nPostSweeps=2, nFinestSweeps=2, tolerance=0, relTol=0, maxIter=cycles)
+           cacheAgglomeration=True, nPreSweeps=0, nPostSweeps=2, nFinestSweeps=2, tolerance=1e-14, relTol=0, maxIter=cycles)
 d_psi.zero()
 print(ldub200.lduMatrix.solver.New("p", A, ctl).solve_device(d_psi, d_src))

@@ -57,9 +57,9 @@ def test_decomposition_matches_global(R):
     assert np.abs(rs - wg.residual(x, g["source"])[0]).max() < 1e-13
 
 
-@pytest.mark.parametrize("R", [2, 4, 8])
+@pytest.mark.parametrize("R", [2, 4, 8, 16, 32])
 def test_local_box_region_equals_decompose(R):
-    n = 8
+    n = 8       # 16 and 32 regions (2x2x4, 2x4x4): the decompositions of the many-core reference arm
     g = meshes.laplacian_system(n, n, n)
     px, py, pz = decompose.split_for(R)
     regs = decompose.decompose(g, decompose.block_partition(n, n, n, px, py, pz), R)
