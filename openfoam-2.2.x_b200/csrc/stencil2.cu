@@ -83,7 +83,9 @@ struct Box2 {
     int nTiles;  // nz * nJ
     int nKg;     // k-groups of W planes
     int W3;      // 0: tile layout [tile][step][lane]; > 0: stacked layout of the register-stacked sweeps, see tile_row
-    int ticks;   // stacked layout: steps + W3 - 1 ticks per (stack, column) group
+    int ticks;   // stacked layout: steps + W3 / blk - 1 ticks per (stack, column) group
+    int blk;     // stacked layout: planes per block (1: every plane lags one tick behind the plane below; b: the b
+                 // planes of a block run the SAME step in a tick, blocks lag one tick), see tile_row
 };
 
 // Row (32 doubles) of step t of the tile (plane k, column J).
@@ -91,11 +93,15 @@ struct Box2 {
 //   stacked layout : [kg = k / W][J][tick = t + p][p = k % W] -- the W rows one warp of sweep3_kernel
 //     needs in one tick (plane p of the stack lags p steps behind plane 0) are adjacent: 256*W bytes per
 //     operand and tick, one contiguous stream per (stack, column) group in both sweep directions.
+//     Blocked (blk = planes per warp of sweep4_kernel<.., BLK = true>): tick = t + p / blk.  The planes of a warp
+//     run the same step in a tick, one after the other (the k-neighbour of the second plane is the value the warp
+//     has just computed): a stack of 16 planes spans 8 ticks instead of 16, at the price of a dependent chain of
+//     blk cells inside a tick.
 __device__ __forceinline__ long long tile_row(const Box2& b, int k, int J, int t)
 {
     if (b.W3 == 0) return (long long)(k * b.nJ + J) * b.steps + t;
     const int kg = k / b.W3, p = k - kg * b.W3;
-    return ((long long)(kg * b.nJ + J) * b.ticks + (t + p)) * b.W3 + p;
+    return ((long long)(kg * b.nJ + J) * b.ticks + (t + p / b.blk)) * b.W3 + p;
 }
 
 __device__ __forceinline__ void g_store(LLW* p, double v, unsigned int tag)
@@ -841,7 +847,7 @@ struct Smem4 {
     int ticket;
 };
 
-template <int W, int M, bool BWD>
+template <int W, int M, bool BWD, bool BLK>
 __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
 {
     constexpr int MW = M * W;
@@ -874,11 +880,12 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
     const bool jIn = BWD ? (J + 1 < nJ) : (J > 0);
     const bool jOut = BWD ? (J > 0) : (J + 1 < nJ);
     const unsigned int epoch = a.epoch;
-    const int nRho = nx + MW - 1;                              // rows of a group's gJ block
+    constexpr int kSpan = BLK ? M : MW;                        // ticks a stack spans: one per plane, blocked one per warp
+    const int nRho = nx + kSpan - 1;                           // rows of a group's gJ block
     auto sigma_of = [&](int s_) { return BWD ? ticks - 1 - s_ : s_; };
     auto k_row = [&](int s_) -> int {
         const int sg = sigma_of(s_);
-        const int t = BWD ? sg - (MW - 1) : sg;
+        const int t = BWD ? sg - (kSpan - 1) : sg;
         return (kIn && t >= 0 && t < steps) ? t : -1;
     };
     auto j_row = [&](int s_) -> int {
@@ -1017,14 +1024,15 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
 #pragma unroll
     for (int p = 0; p < W; p++) {
         // forward: sigma = s, valid for s in [p0+p, p0+p+steps); backward: sigma = ticks-1-s
-        const int lo = p0 + p, hi = p0 + p + steps;             // sigma range
+        const int off = BLK ? warp : p0 + p;                    // tick offset of the plane in the layout
+        const int lo = off, hi = off + steps;                   // sigma range
         yLo[p] = BWD ? ticks - hi : lo;
         yHi[p] = (p0 + p < Wg) ? (BWD ? ticks - lo : hi) : yLo[p];
     }
     // k output of the last warp: forward t = s - (MW-1) >= 0, < steps  -> s in [MW-1, MW-1+steps);
     // backward t = sigma = ticks-1-s < steps -> s in [ticks-steps, ticks)
-    const int kOutLo = (last && kOut) ? (BWD ? ticks - steps : MW - 1) : 0;
-    const int kOutHi = (last && kOut) ? (BWD ? ticks : MW - 1 + steps) : 0;
+    const int kOutLo = (last && kOut) ? (BWD ? ticks - steps : kSpan - 1) : 0;
+    const int kOutHi = (last && kOut) ? (BWD ? ticks : kSpan - 1 + steps) : 0;
     LLW* gKout = a.gK + ((long long)g * steps) * 32 + lane + (long long)(BWD ? steps - 1 : 0) * 32 - (long long)kOutLo * dSig * 32;
     // j output: forward rho = s - 31 in [0, nRho) -> s in [31, 31+nRho); backward rho = ticks-1-s in [0, nRho)
     const int jOutLo = jOut ? (BWD ? ticks - nRho : 31) : 0;
@@ -1162,12 +1170,25 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
                 vj[p] = BWD ? __shfl_down_sync(0xffffffffu, res[p], 1) : __shfl_up_sync(0xffffffffu, res[p], 1);
                 if (JI) vj[p] = (lane == edgeLane) ? ve[p] : vj[p];
             }
+            if (BLK) {
+                // the planes of the warp one after the other, from the plane next to the k input: the k-neighbour
+                // of the others is the value just computed
 #pragma unroll
-            for (int p = 0; p < W; p++) {
-                const double vk = BWD ? (p < W - 1 ? res[p < W - 1 ? p + 1 : p] : vkin) : (p > 0 ? res[p > 0 ? p - 1 : p] : vkin);
-                double acc = __dsub_rn(src[p], __dmul_rn(opk[p], vk));
-                acc = __dsub_rn(acc, __dmul_rn(opj[p], vj[p]));
-                nr[p] = __dsub_rn(acc, __dmul_rn(opi[p], res[p]));
+                for (int pp = 0; pp < W; pp++) {
+                    const int p = BWD ? W - 1 - pp : pp;
+                    const double vk = pp == 0 ? vkin : nr[BWD ? (p + 1 < W ? p + 1 : p) : (p > 0 ? p - 1 : p)];
+                    double acc = __dsub_rn(src[p], __dmul_rn(opk[p], vk));
+                    acc = __dsub_rn(acc, __dmul_rn(opj[p], vj[p]));
+                    nr[p] = __dsub_rn(acc, __dmul_rn(opi[p], res[p]));
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < W; p++) {
+                    const double vk = BWD ? (p < W - 1 ? res[p < W - 1 ? p + 1 : p] : vkin) : (p > 0 ? res[p > 0 ? p - 1 : p] : vkin);
+                    double acc = __dsub_rn(src[p], __dmul_rn(opk[p], vk));
+                    acc = __dsub_rn(acc, __dmul_rn(opj[p], vj[p]));
+                    nr[p] = __dsub_rn(acc, __dmul_rn(opi[p], res[p]));
+                }
             }
 #pragma unroll
             for (int p = 0; p < W; p++) res[p] = nr[p];
@@ -1558,8 +1579,15 @@ int state2(ldu_matrix* m, State2** out)
         s->M4 = gen == 4 ? pick_M4(b.nz) : 0;
         s->W = gen == 4 ? (s->M4 == 16 ? 16 : 2 * s->M4) : v3 ? pick_W3(b.nz) : pick_W(b.nz);
         b.nKg = (b.nz + s->W - 1) / s->W;
+        // the two planes of a chain warp run the same step in a tick (blocked layout, see tile_row); LDU_STENCIL_BLK=1:
+        // every plane one tick behind the plane below, as in the third generation
+        b.blk = 1;
+        if (gen == 4 && s->M4 != 16) {
+            const char* be = getenv("LDU_STENCIL_BLK");
+            b.blk = (be && atoi(be) == 1) ? 1 : 2;
+        }
         b.W3 = v3 ? s->W : 0;
-        b.ticks = b.steps + s->W - 1;
+        b.ticks = b.steps + s->W / b.blk - 1;
         s->padded = v3 ? (long long)b.nKg * b.nJ * b.ticks * s->W * 32 : (long long)b.nTiles * b.steps * 32;
         cudaStream_t st = m->ctx->stream;
         LDU_TRY(alloc_padded2((void**)&s->Y, (size_t)s->padded, sizeof(double), st));
@@ -1668,13 +1696,13 @@ int launch_sweeps(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
     return LDU_OK;
 }
 
-template <int W, int M>
+template <int W, int M, bool BLK>
 int launch_sweeps4(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
 {
     const size_t smem = sizeof(Smem4<W, M>);
     if (!s->attrSet) {
-        LDU_CUDA(cudaFuncSetAttribute(sweep4_kernel<W, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LDU_CUDA(cudaFuncSetAttribute(sweep4_kernel<W, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LDU_CUDA(cudaFuncSetAttribute(sweep4_kernel<W, M, false, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LDU_CUDA(cudaFuncSetAttribute(sweep4_kernel<W, M, true, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         s->attrSet = true;
     }
     const int grid = s->b.nKg * s->b.nJ;
@@ -1690,7 +1718,7 @@ int launch_sweeps4(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
     a.pk = P.F[0];
     a.pj = P.F[1];
     a.pi = P.F[2];
-    if (!(only && only[0] == 'b')) sweep4_kernel<W, M, false><<<grid, (M + 2) * 32, smem, st>>>(a);
+    if (!(only && only[0] == 'b')) sweep4_kernel<W, M, false, BLK><<<grid, (M + 2) * 32, smem, st>>>(a);
     count_launch();
     LDU_CUDA(cudaGetLastError());
     if (a.trace) {   // debug only: per-warp timeline of the forward sweep
@@ -1711,7 +1739,7 @@ int launch_sweeps4(ldu_matrix* m, State2* s, S2Args& a, const Products& P)
     a.pk = P.B[0];
     a.pj = P.B[1];
     a.pi = P.B[2];
-    if (!(only && only[0] == 'f')) sweep4_kernel<W, M, true><<<grid, (M + 2) * 32, smem, st>>>(a);
+    if (!(only && only[0] == 'f')) sweep4_kernel<W, M, true, BLK><<<grid, (M + 2) * 32, smem, st>>>(a);
     count_launch();
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;
@@ -1830,10 +1858,13 @@ static int apply_core(ldu_matrix* m, const double* rD, const double* coefF, cons
     a.gK = s->gK;
     a.gJ = s->gJ;
     a.ticket = s->ticket;
-    if (s->gen == 4 && s->M4 == 16) LDU_TRY((launch_sweeps4<1, 16>(m, s, a, P)));
-    else if (s->gen == 4 && s->M4 == 8) LDU_TRY((launch_sweeps4<2, 8>(m, s, a, P)));
-    else if (s->gen == 4 && s->M4 == 4) LDU_TRY((launch_sweeps4<2, 4>(m, s, a, P)));
-    else if (s->gen == 4) LDU_TRY((launch_sweeps4<2, 2>(m, s, a, P)));
+    if (s->gen == 4 && s->M4 == 16) LDU_TRY((launch_sweeps4<1, 16, false>(m, s, a, P)));
+    else if (s->gen == 4 && s->M4 == 8 && s->b.blk == 2) LDU_TRY((launch_sweeps4<2, 8, true>(m, s, a, P)));
+    else if (s->gen == 4 && s->M4 == 4 && s->b.blk == 2) LDU_TRY((launch_sweeps4<2, 4, true>(m, s, a, P)));
+    else if (s->gen == 4 && s->b.blk == 2) LDU_TRY((launch_sweeps4<2, 2, true>(m, s, a, P)));
+    else if (s->gen == 4 && s->M4 == 8) LDU_TRY((launch_sweeps4<2, 8, false>(m, s, a, P)));
+    else if (s->gen == 4 && s->M4 == 4) LDU_TRY((launch_sweeps4<2, 4, false>(m, s, a, P)));
+    else if (s->gen == 4) LDU_TRY((launch_sweeps4<2, 2, false>(m, s, a, P)));
     else if (s->b.W3 == 16) LDU_TRY(launch_sweeps3<16>(m, s, a, P));
     else if (s->b.W3 == 12) LDU_TRY(launch_sweeps3<12>(m, s, a, P));
     else if (s->b.W3 == 8) LDU_TRY(launch_sweeps3<8>(m, s, a, P));

@@ -109,7 +109,7 @@ def test_smoothers_bit_exact(ctx, system, sm):
 
 
 @pytest.mark.parametrize("W", ["4", "8", "12", "15", "16"])
-@pytest.mark.parametrize("version", ["1", "2", "3", "4"])
+@pytest.mark.parametrize("version", ["1", "2", "3", "4", "4u"])
 def test_box_sweeps_all_stack_heights(ctx, W, version, monkeypatch):
     """Structured-box sweeps with every stack height (planes per CTA / per warp) and all three kernel
     generations: DIC and DILU applications stay bit-identical to the reference order.
@@ -119,12 +119,13 @@ def test_box_sweeps_all_stack_heights(ctx, W, version, monkeypatch):
         pytest.skip("stack height only exists in the second and third generation")
     if (version == "2" and W == "12") or (version == "3" and W == "15"):
         pytest.skip("not a stack height of this generation")
-    if version == "4":      # chained warps: W selects the number of warps per CTA (2 planes each)
-        if W not in ("4", "8", "16"):
+    if version in ("4", "4u"):  # chained warps: W selects the number of warps per CTA (2 planes each);
+        if W not in ("4", "8", "16"):                       # "4u": the planes of a warp one tick apart (unblocked)
             pytest.skip("generation 4 has 2, 4 or 8 warps of 2 planes")
         monkeypatch.setenv("LDU_STENCIL_M", str(int(W) // 2))
+        monkeypatch.setenv("LDU_STENCIL_BLK", "1" if version == "4u" else "2")
     monkeypatch.setenv("LDU_STENCIL_W", W)
-    monkeypatch.setenv("LDU_STENCIL", version)
+    monkeypatch.setenv("LDU_STENCIL", version[0])
     O = _oracle()
     for kw, pre in ((dict(nx=37, ny=70, nz=40, variable=True), "DIC"),
                     (dict(nx=3, ny=33, nz=40, variable=True, asym=0.3), "DILU")):
@@ -256,8 +257,9 @@ def test_full_size_box_sweeps_match_generic_path(ctx, monkeypatch):
     s = meshes.laplacian_system(n, n, n, variable=True)
     r = np.sin(0.37 * np.arange(s["nCells"]))
     out = {}
-    for ver in ("4", "3", "2", "0"):
-        monkeypatch.setenv("LDU_STENCIL", ver)
+    for ver in ("4", "4u", "3", "2", "0"):
+        monkeypatch.setenv("LDU_STENCIL", ver[0])
+        monkeypatch.setenv("LDU_STENCIL_BLK", "1" if ver == "4u" else "2")
         A = _matrix(ctx, s)
         P = ldub200.lduMatrix.preconditioner.New(A, "DIC")
         out[ver] = P.precondition(r)
@@ -265,7 +267,8 @@ def test_full_size_box_sweeps_match_generic_path(ctx, monkeypatch):
             again = P.precondition(r)      # rings, tickets and epochs are reused
             assert np.array_equal(again, out[ver])
         A.destroy()
-    assert np.array_equal(out["4"], out["0"])     # chained register-stacked warps
+    assert np.array_equal(out["4"], out["0"])     # chained register-stacked warps, two planes per tick (default)
+    assert np.array_equal(out["4u"], out["0"])    # the same, planes one tick apart
     assert np.array_equal(out["3"], out["0"])     # register-stacked warps
     assert np.array_equal(out["2"], out["0"])     # plane-stacked CTAs
     assert np.isfinite(out["3"]).all() and np.abs(out["3"]).max() > 0
