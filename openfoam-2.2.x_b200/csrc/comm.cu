@@ -29,10 +29,6 @@ CommDev comm_dev(const ldu_context* ctx)
     return c;
 }
 
-struct IfaceDev {
-    int offset, n, nbrRank, nbrInterface;
-};
-
 // psi[faceCells] of every interface -> the neighbour's window, then publish the
 // epoch to every neighbour (last block).
 __global__ void __launch_bounds__(kBlock) halo_put_kernel(CommDev c, const IfaceDev* __restrict__ ifs,
@@ -190,6 +186,18 @@ int comm_halo_recv(ldu_matrix* m, bool guarded)
                                                           m->d_scalars, guarded);
     count_launch();
     LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+// the validated device table of a matrix's interfaces, for kernels that exchange halos themselves (gamg.cu)
+int comm_halo_table(ldu_matrix* m, const IfaceDev** tab)
+{
+    *tab = nullptr;
+    if (!m->nIfFaces) return LDU_OK;
+    dim3 grid;
+    IfaceDev* t = nullptr;
+    LDU_TRY(halo_grid(m, grid, &t));
+    *tab = t;
     return LDU_OK;
 }
 

@@ -16,6 +16,15 @@
 
 namespace ldu {
 
+// A double and its message tag in one 16-byte word, each 8-byte half carrying the tag (NCCL-LL style): the value
+// IS the flag, so a message costs one one-way NVLink latency -- no system fence, no separate release store.  Used by
+// the coupled coarsest-level kernel (gamg.cu), whose iterations are nothing but such messages.
+struct alignas(16) LLMsg {
+    unsigned int lo, t0, hi, t1;
+};
+constexpr int kLLIfs = 16;      // interfaces per rank served by the LL halo words
+constexpr int kLLFaces = 32;    // faces per interface
+
 struct WindowHeader {
     unsigned long long redEpoch;                    // local counters (owner writes)
     unsigned long long haloEpoch;
@@ -24,7 +33,32 @@ struct WindowHeader {
     unsigned long long haloSeq[2][kMaxRanks];       // written by peers: "my halos of epoch e landed"
     unsigned int haloTicket;
     unsigned int pad;
+    LLMsg redLL[2][kMaxRanks][2];                  // written by peers: all-reduce partials, tagged with the epoch
+    LLMsg haloLL[2][kLLIfs][kLLFaces];             // written by peers: halo values of small interfaces, tagged
 };
+
+__device__ __forceinline__ void ll_store_sys(LLMsg* p, double v, unsigned int tag)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)b), "r"(tag),
+                 "r"((unsigned int)(b >> 32)), "r"(tag)
+                 : "memory");
+}
+
+// poll a word of this rank's own window until both halves carry `tag`; false on time-out
+__device__ __forceinline__ bool ll_wait_sys(const LLMsg* p, unsigned int tag, long long timeoutCycles, double& v)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned int lo, a, hi, b;
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(a), "=r"(hi), "=r"(b) : "l"(p) : "memory");
+        if (a == tag && b == tag) {
+            v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+            return true;
+        }
+        if (clock64() - t0 > timeoutCycles) return false;
+    }
+}
 
 struct CommDev {
     int rank;
@@ -117,8 +151,9 @@ __device__ __forceinline__ void comm_allreduce_dev(const CommDev& c, double (&v)
 // side by side instead of one after the other (at 8 ranks the serial version cost ~3x the NVLink round trip per
 // reduction, three reductions per PCG iteration).  v is taken from lane 0; the sum is formed in rank order by
 // every lane alike, so the result is bit-identical to comm_allreduce_dev's and identical on all ranks.
+// Returns false (on every lane) after a time-out.
 template <int NRED>
-__device__ __forceinline__ void comm_allreduce_warp(const CommDev& c, double (&v)[NRED], SolverScalars* S)
+__device__ __forceinline__ bool comm_allreduce_warp(const CommDev& c, double (&v)[NRED], SolverScalars* S)
 {
     const int lane = threadIdx.x & 31;
     WindowHeader* me = win_hdr(c, c.rank);
@@ -150,7 +185,7 @@ __device__ __forceinline__ void comm_allreduce_warp(const CommDev& c, double (&v
     }
     if (!__all_sync(0xffffffffu, ok)) {
         if (S && lane == 0) { S->commError = 1; S->done = 1; }
-        return;
+        return false;
     }
     double tot[NRED];
 #pragma unroll
@@ -161,8 +196,60 @@ __device__ __forceinline__ void comm_allreduce_warp(const CommDev& c, double (&v
     }
 #pragma unroll
     for (int k = 0; k < NRED; k++) v[k] = tot[k];
+    return true;
+}
+
+// comm_allreduce_warp with tagged words (NRED <= 2): lane r sends the partials to rank r and polls rank r's words
+// in its own window; same rank-order sum, same epoch counter (the two flavours may be mixed: a rank is never more
+// than one reduction ahead of another, so the two parity halves of either buffer are enough).
+template <int NRED>
+__device__ __forceinline__ bool comm_allreduce_warp_ll(const CommDev& c, double (&v)[NRED], SolverScalars* S)
+{
+    static_assert(NRED <= 2, "redLL holds two words per rank");
+    const int lane = threadIdx.x & 31;
+    WindowHeader* me = win_hdr(c, c.rank);
+    unsigned long long epoch = 0;
+    if (lane == 0) {
+        epoch = me->redEpoch + 1;
+        me->redEpoch = epoch;
+    }
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
+    const int par = (int)(epoch & 1ull);
+    const unsigned int tag = (unsigned int)epoch;
+    double x[NRED];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < NRED; k++) x[k] = __shfl_sync(0xffffffffu, v[k], 0);
+    if (lane < c.nRanks) {
+        WindowHeader* w = win_hdr(c, lane);
+#pragma unroll
+        for (int k = 0; k < NRED; k++) ll_store_sys(&w->redLL[par][c.rank][k], x[k], tag);
+#pragma unroll
+        for (int k = 0; k < NRED; k++) ok = ok && ll_wait_sys(&me->redLL[par][lane][k], tag, c.timeoutCycles, x[k]);
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+        if (S && lane == 0) { S->commError = 1; S->done = 1; }
+        return false;
+    }
+    double tot[NRED];
+#pragma unroll
+    for (int k = 0; k < NRED; k++) tot[k] = __shfl_sync(0xffffffffu, x[k], 0);
+    for (int r = 1; r < c.nRanks; r++) {
+#pragma unroll
+        for (int k = 0; k < NRED; k++) tot[k] = __dadd_rn(tot[k], __shfl_sync(0xffffffffu, x[k], r));
+    }
+#pragma unroll
+    for (int k = 0; k < NRED; k++) v[k] = tot[k];
+    return true;
 }
 
 CommDev comm_dev(const ldu_context* ctx);
+
+// one coupled interface of a matrix: faces [offset, offset+n) of the concatenated interface arrays go to slot
+// nbrInterface of rank nbrRank's window
+struct IfaceDev {
+    int offset, n, nbrRank, nbrInterface;
+};
+int comm_halo_table(ldu_matrix* m, const IfaceDev** tab);
 
 }  // namespace ldu
