@@ -41,7 +41,8 @@ static int upload(ldu_context* ctx, T** d, const T* h, size_t n, size_t pad = 0)
 // ---------------------------------------------------------------------------
 namespace {
 constexpr int kStageThreads = 12;    // upper bound; LDU_STAGE_THREADS picks fewer (default 8)
-constexpr size_t kStageChunk = 4u << 20;
+constexpr size_t kStageChunk = 4u << 20;            // size of a pinned staging buffer
+constexpr size_t kStageChunkDefault = 4u << 20;     // bytes staged per copy
 constexpr size_t kStageMin = 1u << 20;     // below this a plain copy is as fast
 
 struct StageWorker {
@@ -86,7 +87,13 @@ int staged_copy(ldu_context* ctx, unsigned char* dst, const unsigned char* src, 
     StagePool* sp = nullptr;
     LDU_TRY(stage_pool(ctx, &sp));
     LDU_CUDA(cudaStreamSynchronize(ctx->stream));     // ordered after what is queued on the context's stream
-    const size_t nChunks = (bytes + kStageChunk - 1) / kStageChunk;
+    // LDU_STAGE_CHUNK_KB: bytes staged per copy (at most the size of the pinned buffers)
+    static const size_t chunk = [] {
+        const char* e = getenv("LDU_STAGE_CHUNK_KB");
+        const size_t v = e ? (size_t)atol(e) << 10 : kStageChunkDefault;
+        return std::max<size_t>(64u << 10, std::min(v, kStageChunk));
+    }();
+    const size_t nChunks = (bytes + chunk - 1) / chunk;
     static const int wanted = [] {
         const char* e = getenv("LDU_STAGE_THREADS");
         const int hw = (int)std::thread::hardware_concurrency();
@@ -103,7 +110,7 @@ int staged_copy(ldu_context* ctx, unsigned char* dst, const unsigned char* src, 
         size_t pending[2] = {0, 0}, pendingOff[2] = {0, 0};      // D2H: bytes waiting in buffer b
         int use = 0;
         for (size_t k = t; k < nChunks && e == cudaSuccess; k += nThreads, use ^= 1) {
-            const size_t off = k * kStageChunk, n = std::min(kStageChunk, bytes - off);
+            const size_t off = k * chunk, n = std::min(chunk, bytes - off);
             if (toDevice) {
                 e = cudaEventSynchronize(w.ev[use]);             // the copy that last used this buffer is done
                 if (e != cudaSuccess) break;

@@ -847,7 +847,7 @@ struct Smem4 {
     int ticket;
 };
 
-template <int W, int M, bool BWD, bool BLK>
+template <int W, int M, bool BWD, bool BLK, bool DIV = false>
 __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
 {
     constexpr int MW = M * W;
@@ -1177,9 +1177,18 @@ __global__ void __launch_bounds__((M + 2) * 32, 1) sweep4_kernel(S2Args a)
                 for (int pp = 0; pp < W; pp++) {
                     const int p = BWD ? W - 1 - pp : pp;
                     const double vk = pp == 0 ? vkin : nr[BWD ? (p + 1 < W ? p + 1 : p) : (p > 0 ? p - 1 : p)];
-                    double acc = __dsub_rn(src[p], __dmul_rn(opk[p], vk));
-                    acc = __dsub_rn(acc, __dmul_rn(opj[p], vj[p]));
-                    nr[p] = __dsub_rn(acc, __dmul_rn(opi[p], res[p]));
+                    if (DIV) {
+                        // the recurrence of the DIC / DILU diagonal, rD[u] -= upper*lower / rD[l] in face order
+                        // (DICPreconditioner.C:66-84): the operands are the products upper*lower, the values the
+                        // diagonal itself.  A neighbour that does not exist has operand 0 and value 0: divide by 1.
+                        double acc = __dsub_rn(src[p], __ddiv_rn(opk[p], vk == 0.0 ? 1.0 : vk));
+                        acc = __dsub_rn(acc, __ddiv_rn(opj[p], vj[p] == 0.0 ? 1.0 : vj[p]));
+                        nr[p] = __dsub_rn(acc, __ddiv_rn(opi[p], res[p] == 0.0 ? 1.0 : res[p]));
+                    } else {
+                        double acc = __dsub_rn(src[p], __dmul_rn(opk[p], vk));
+                        acc = __dsub_rn(acc, __dmul_rn(opj[p], vj[p]));
+                        nr[p] = __dsub_rn(acc, __dmul_rn(opi[p], res[p]));
+                    }
                 }
             } else {
 #pragma unroll
@@ -1435,19 +1444,27 @@ __global__ void __launch_bounds__(256) products2_kernel(Box2 b, int nBlk, const 
         if (j < b.ny && i >= 0 && i < b.nx) {
             const int c = (k * b.ny + j) * b.nx + i;
             const int hasI = i < b.nx - 1, hasJ = j < b.ny - 1, hasK = k < b.nz - 1;
-            const double rr = rD[c];
+            const double rr = HALF == 2 ? 0.0 : rD[c];
             if (HALF == 0) {
                 // faces this cell owns, in the order +i, +j, +k
                 const int os = ownerStart[c];
                 v2 = hasI ? __dmul_rn(rr, coefB[os]) : 0.0;
                 v1 = hasJ ? __dmul_rn(rr, coefB[os + hasI]) : 0.0;
                 v0 = hasK ? __dmul_rn(rr, coefB[os + hasI + hasJ]) : 0.0;
-            } else {
+            } else if (HALF == 1) {
                 // faces where it is the upper cell: the +k / +j / +i face of the cell below /
                 // behind / to the left (those cells have the same i, j flags where it matters)
                 v0 = k > 0 ? __dmul_rn(rr, coefF[ownerStart[c - b.nx * b.ny] + hasI + hasJ]) : 0.0;
                 v1 = j > 0 ? __dmul_rn(rr, coefF[ownerStart[c - b.nx] + hasI]) : 0.0;
                 v2 = i > 0 ? __dmul_rn(rr, coefF[ownerStart[c - 1]]) : 0.0;
+            } else {
+                // the same faces for the recurrence of the diagonal: upper*lower of the face (rD is not read)
+                const int fk = k > 0 ? ownerStart[c - b.nx * b.ny] + hasI + hasJ : 0;
+                const int fj = j > 0 ? ownerStart[c - b.nx] + hasI : 0;
+                const int fi = i > 0 ? ownerStart[c - 1] : 0;
+                v0 = k > 0 ? __dmul_rn(coefF[fk], coefB[fk]) : 0.0;
+                v1 = j > 0 ? __dmul_rn(coefF[fj], coefB[fj]) : 0.0;
+                v2 = i > 0 ? __dmul_rn(coefF[fi], coefB[fi]) : 0.0;
             }
         }
         s[0][r][lane] = v0;
@@ -1455,7 +1472,7 @@ __global__ void __launch_bounds__(256) products2_kernel(Box2 b, int nBlk, const 
         s[2][r][lane] = v2;
     }
     __syncthreads();
-    double* const o0 = HALF == 0 ? P.B[0] : P.F[0];
+    double* const o0 = HALF == 0 ? P.B[0] : P.F[0];     // HALF 2 writes the forward arrays too
     double* const o1 = HALF == 0 ? P.B[1] : P.F[1];
     double* const o2 = HALF == 0 ? P.B[2] : P.F[2];
     for (int x = wid; x < 32; x += 8) {
@@ -1491,7 +1508,7 @@ struct State2 {
     unsigned int epoch = 0;
     ProductSlot slot[2];
     long long useClock = 0;
-    bool attrSet = false;
+    bool attrSet = false, attrSetRD = false;
     const double* yReadyFor = nullptr;   // Y already holds rD * (this vector), written by xr_pack2_kernel
     unsigned long long* trace = nullptr;
 };
@@ -1882,6 +1899,85 @@ static int apply_core(ldu_matrix* m, const double* rD, const double* coefF, cons
     } else {
         unpack2_kernel<<<gridT, 256, 0, st>>>(s->b, nBlk, s->Y, w, m->d_scalars);
     }
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+
+namespace {
+template <int W, int M>
+int launch_rD4(ldu_matrix* m, State2* s, S2Args& a)
+{
+    const size_t smem = sizeof(Smem4<W, M>);
+    if (!s->attrSetRD) {
+        LDU_CUDA(cudaFuncSetAttribute(sweep4_kernel<W, M, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s->attrSetRD = true;
+    }
+    a.epoch = ++s->epoch;
+    sweep4_kernel<W, M, false, true, true><<<s->b.nKg * s->b.nJ, (M + 2) * 32, smem, m->ctx->stream>>>(a);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    return LDU_OK;
+}
+}  // namespace
+
+// is the recurrence of the DIC / DILU diagonal available on the box path?  (fourth generation, blocked layout)
+bool stencil2_rD_available(ldu_matrix* m)
+{
+    if (stencil_version(m) != 2) return false;
+    static const bool off = getenv("LDU_STENCIL_RD") && getenv("LDU_STENCIL_RD")[0] == '0';
+    if (off) return false;
+    State2* s;
+    if (state2(m, &s) != LDU_OK) return false;
+    return s->gen == 4 && s->b.blk == 2;
+}
+
+// rD = diag; rD[u] -= upper[f]*lower[f] / rD[l] for the faces in order (DICPreconditioner.C:66-84 with lower = upper,
+// DILUPreconditioner.C:66-85): one forward sweep of the chained warps with a division in place of the product.
+// The reciprocal is left to the caller, as in calc_reciprocal_D.
+int stencil2_rD(ldu_matrix* m, double* rD, const double* upper, const double* lower)
+{
+    State2* s;
+    LDU_TRY(state2(m, &s));
+    cudaStream_t st = m->ctx->stream;
+    // the products go into the forward arrays of a product slot; the sweeps' own products are computed after rD
+    // (they need it), so the slot is simply marked stale
+    ProductSlot& ps = s->slot[s->slot[0].lastUse <= s->slot[1].lastUse ? 0 : 1];
+    if (!ps.allocated) {
+        for (int d = 0; d < 3; d++) {
+            LDU_TRY(alloc_padded2((void**)&ps.P.F[d], (size_t)s->padded, sizeof(double), st));
+            LDU_TRY(alloc_padded2((void**)&ps.P.B[d], (size_t)s->padded, sizeof(double), st));
+        }
+        ps.allocated = true;
+    }
+    ps.sweepGen = -1;
+    ps.rD = nullptr;
+    const int nBlk = (s->b.steps + 31) / 32;
+    const int gridT = s->b.nTiles * nBlk;
+    products2_kernel<2><<<gridT, 256, 0, st>>>(s->b, nBlk, m->d_ownerStart, nullptr, upper, lower, ps.P);
+    count_launch();
+    pack2_kernel<false><<<gridT, 256, 0, st>>>(s->b, nBlk, m->d_diag, nullptr, s->Y, nullptr);
+    count_launch();
+    LDU_CUDA(cudaGetLastError());
+    LDU_CUDA(cudaMemsetAsync(s->ticket, 0, 2 * sizeof(unsigned int), st));
+    s->yReadyFor = nullptr;
+    S2Args a;
+    a.dbg = 0;
+    a.S = m->d_scalars;
+    a.guarded = 0;
+    a.b = s->b;
+    a.Y = s->Y;
+    a.gK = s->gK;
+    a.gJ = s->gJ;
+    a.ticket = s->ticket;
+    a.trace = nullptr;
+    a.pk = ps.P.F[0];
+    a.pj = ps.P.F[1];
+    a.pi = ps.P.F[2];
+    if (s->M4 == 8) LDU_TRY((launch_rD4<2, 8>(m, s, a)));
+    else if (s->M4 == 4) LDU_TRY((launch_rD4<2, 4>(m, s, a)));
+    else LDU_TRY((launch_rD4<2, 2>(m, s, a)));
+    unpack2_kernel<<<gridT, 256, 0, st>>>(s->b, nBlk, s->Y, rD, nullptr);
     count_launch();
     LDU_CUDA(cudaGetLastError());
     return LDU_OK;

@@ -367,6 +367,10 @@ int calc_reciprocal_D(ldu_matrix* m, double* rD, bool dilu)
 {
     m->sweepGen++;
     const double* lower = dilu ? m->d_lower : m->d_upper;  // DIC: upper*upper (DICPreconditioner.C:73)
+    if (stencil2_rD_available(m)) {      // blockMesh box: one forward sweep of the chained warps
+        LDU_TRY(stencil2_rD(m, rD, m->d_upper, lower));
+        return launch_map<false>(m, m->nCells, RecipMap{rD});
+    }
     if (use_dataflow(m)) {
         LDU_TRY(flow_rD(m, rD, m->d_upper, lower));
         return launch_map<false>(m, m->nCells, RecipMap{rD});

@@ -46,6 +46,9 @@ int stencil2_apply(ldu_matrix* m, const double* rD, const double* coefF, const d
 // fused with |r|_1 (EpiResidual) and with the packing of rD*rA for the next application
 int stencil2_apply_dot(ldu_matrix* m, const double* rD, const double* coefF, const double* coefB, const double* r,
                        double* w, const double* dotWith);
+// the recurrence of the DIC / DILU diagonal on a blockMesh box (without the final reciprocal)
+bool stencil2_rD_available(ldu_matrix* m);
+int stencil2_rD(ldu_matrix* m, double* rD, const double* upper, const double* lower);
 int stencil2_xr_pack(ldu_matrix* m, const double* rD, double* psi, double* rA, const double* pA, const double* wA);
 void stencil2_invalidate(ldu_matrix* m);   // the tile image of rD*rA is stale (a new solve starts)
 
