@@ -10,6 +10,7 @@
 // window (CUDA IPC mapping, NVLink/NVSwitch P2P stores) from inside the kernels
 // that produce them; the consumer spins on an epoch flag in its own HBM.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "comm.cuh"
@@ -26,6 +27,8 @@ CommDev comm_dev(const ldu_context* ctx)
     c.maxInterfaces = ctx->comm.maxInterfaces;
     c.slotStride = ctx->comm.slotStride;
     c.timeoutCycles = 20000000000ll;  // ~10 s: fail loudly instead of hanging the GPU
+    static const int llRed = (getenv("LDU_RED_LL") && getenv("LDU_RED_LL")[0] == '0') ? 0 : 1;
+    c.llRed = llRed;
     return c;
 }
 

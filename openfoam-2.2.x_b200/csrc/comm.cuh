@@ -67,6 +67,7 @@ struct CommDev {
     int maxInterfaces;
     long long slotStride;         // doubles per interface slot
     long long timeoutCycles;
+    int llRed;                    // all-reduces of one or two sums use the tagged words (LDU_RED_LL=0: the mailboxes)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)

@@ -83,7 +83,15 @@ __device__ __forceinline__ void reduce_tail(double (&acc)[NRED], const ReduceCtx
     block_sum<NRED>(tot, smem);
     if (threadIdx.x < 32) {      // the first warp, converged (block_sum ends with a barrier); totals valid in lane 0
         if (threadIdx.x == 0) *rc.ticket = 0u;  // re-arm for the next launch on this stream
-        if (rc.comm.nRanks > 1) comm_allreduce_warp<NRED>(rc.comm, tot, rc.S);
+        if (rc.comm.nRanks > 1) {
+            // one or two sums travel as tagged words (one one-way NVLink latency), more through the mailboxes
+            if constexpr (NRED <= 2) {
+                if (rc.comm.llRed) comm_allreduce_warp_ll<NRED>(rc.comm, tot, rc.S);
+                else comm_allreduce_warp<NRED>(rc.comm, tot, rc.S);
+            } else {
+                comm_allreduce_warp<NRED>(rc.comm, tot, rc.S);
+            }
+        }
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int k = 0; k < NRED; k++) rc.red[k] = tot[k];
