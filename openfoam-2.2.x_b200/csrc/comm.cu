@@ -41,9 +41,8 @@ __global__ void __launch_bounds__(kBlock) halo_put_kernel(CommDev c, const Iface
 {
     if (guard && guard->done) return;
     WindowHeader* me = win_hdr(c, c.rank);
-    const unsigned long long epoch = me->haloEpoch + 1;
-    const int par = (int)(epoch & 1ull);
     const IfaceDev it = ifs[blockIdx.y];
+    const int par = (int)((me->haloSent[it.nbrRank] + 1ull) & 1ull);     // the pair's next exchange
     double* dst = win_halo(c, it.nbrRank, par, it.nbrInterface);
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < it.n; i += gridDim.x * kBlock)
         dst[i] = psi[ifCells[it.offset + i]];
@@ -59,10 +58,15 @@ __global__ void __launch_bounds__(kBlock) halo_put_kernel(CommDev c, const Iface
     if (threadIdx.x == 0) {
         __threadfence_system();
         me->haloTicket = 0u;
-        me->haloEpoch = epoch;
         for (int k = 0; k < nIfs; k++) {
-            // one flag per source rank; repeated stores of the same epoch are harmless
-            st_release_sys(&win_hdr(c, ifs[k].nbrRank)->haloSeq[par][c.rank], epoch);
+            // one counter and one flag per neighbour rank, however many interfaces lead to it
+            const int r = ifs[k].nbrRank;
+            bool first = true;
+            for (int j = 0; j < k; j++) first = first && ifs[j].nbrRank != r;
+            if (!first) continue;
+            const unsigned long long epoch = me->haloSent[r] + 1ull;
+            me->haloSent[r] = epoch;
+            st_release_sys(&win_hdr(c, r)->haloSeq[(int)(epoch & 1ull)][c.rank], epoch);
         }
     }
 }
@@ -75,13 +79,14 @@ __global__ void __launch_bounds__(kBlock) halo_recv_kernel(CommDev c, const Ifac
 {
     if (guarded && S->done) return;
     WindowHeader* me = win_hdr(c, c.rank);
-    const unsigned long long epoch = me->haloEpoch;
-    const int par = (int)(epoch & 1ull);
     __shared__ bool ok;
     if (threadIdx.x == 0) {
         ok = true;
-        for (int k = 0; k < nIfs && ok; k++)
-            ok = wait_epoch(&me->haloSeq[par][ifs[k].nbrRank], epoch, c.timeoutCycles);
+        for (int k = 0; k < nIfs && ok; k++) {
+            // the neighbour's message of the exchange this rank has just sent its own for
+            const unsigned long long epoch = me->haloSent[ifs[k].nbrRank];
+            ok = wait_epoch(&me->haloSeq[(int)(epoch & 1ull)][ifs[k].nbrRank], epoch, c.timeoutCycles);
+        }
         if (!ok) {
             S->commError = 1;
             S->done = 1;
@@ -90,6 +95,7 @@ __global__ void __launch_bounds__(kBlock) halo_recv_kernel(CommDev c, const Ifac
     __syncthreads();
     if (!ok) return;
     const IfaceDev it = ifs[blockIdx.y];
+    const int par = (int)(me->haloSent[it.nbrRank] & 1ull);
     const double* src = win_halo(c, c.rank, par, blockIdx.y);
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < it.n; i += gridDim.x * kBlock)
         recv[it.offset + i] = ld_volatile_f64(src + i);

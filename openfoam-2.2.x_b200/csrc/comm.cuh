@@ -8,8 +8,9 @@
 //
 // Window layout (identical on every rank):
 //   WindowHeader | halo[2][maxInterfaces][slotStride] doubles
-// Every message carries a monotonically increasing epoch; two parity halves make
-// a slot reusable as soon as the NEXT exchange has completed.
+// Every message carries a monotonically increasing epoch (halos: one counter per pair of ranks, reductions: one
+// per rank, all ranks take part in every reduction); two parity halves make a slot reusable as soon as the NEXT
+// exchange has completed.
 #pragma once
 
 #include "ldu_internal.h"
@@ -27,7 +28,9 @@ constexpr int kLLFaces = 32;    // faces per interface
 
 struct WindowHeader {
     unsigned long long redEpoch;                    // local counters (owner writes)
-    unsigned long long haloEpoch;
+    unsigned long long haloSent[kMaxRanks];         // halo exchanges done with rank r, counted per PAIR of ranks: a rank
+                                                    // whose matrix has no face coupled to r does not take part and
+                                                    // does not fall out of step (both ends of a pair count alike)
     unsigned long long redSeq[2][kMaxRanks];        // written by peers
     double redVal[2][kMaxRanks][kRedSlots];
     unsigned long long haloSeq[2][kMaxRanks];       // written by peers: "my halos of epoch e landed"

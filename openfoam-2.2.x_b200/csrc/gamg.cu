@@ -841,29 +841,35 @@ __device__ bool coupled_halo_ll(const CoupledArgs& A, const double* x)
     const int lane = threadIdx.x & 31;
     const CommDev& c = A.comm;
     WindowHeader* me = win_hdr(c, c.rank);
-    unsigned long long epoch = 0;
-    if (lane == 0) {
-        epoch = me->haloEpoch + 1;
-        me->haloEpoch = epoch;
-    }
-    epoch = __shfl_sync(0xffffffffu, epoch, 0);
-    const int par = (int)(epoch & 1ull);
-    const unsigned int tag = (unsigned int)epoch;
     __syncwarp();      // x was written by lane 0
+    // one exchange per neighbour rank (counted per pair, see WindowHeader::haloSent): the tag of interface k
     for (int k = 0; k < A.nIfs; k++) {
         const IfaceDev it = A.ifs[k];
-        if (lane < it.n) ll_store_sys(&win_hdr(c, it.nbrRank)->haloLL[par][it.nbrInterface][lane], x[A.ifCells[it.offset + lane]], tag);
+        const unsigned long long epoch = me->haloSent[it.nbrRank] + 1ull;
+        if (lane < it.n)
+            ll_store_sys(&win_hdr(c, it.nbrRank)->haloLL[(int)(epoch & 1ull)][it.nbrInterface][lane],
+                         x[A.ifCells[it.offset + lane]], (unsigned int)epoch);
     }
     bool ok = true;
     for (int k = 0; k < A.nIfs; k++) {
         const IfaceDev it = A.ifs[k];
+        const unsigned long long epoch = me->haloSent[it.nbrRank] + 1ull;
         double v = 0.0;
         if (lane < it.n) {
-            ok = ok && ll_wait_sys(&me->haloLL[par][k][lane], tag, c.timeoutCycles, v);
+            ok = ok && ll_wait_sys(&me->haloLL[(int)(epoch & 1ull)][k][lane], (unsigned int)epoch, c.timeoutCycles, v);
             A.recv[it.offset + lane] = v;
         }
     }
     ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    if (lane == 0) {
+        for (int k = 0; k < A.nIfs; k++) {
+            const int r = A.ifs[k].nbrRank;
+            bool first = true;
+            for (int j = 0; j < k; j++) first = first && A.ifs[j].nbrRank != r;
+            if (first) me->haloSent[r] = me->haloSent[r] + 1ull;
+        }
+    }
     __syncwarp();
     return ok;
 }
@@ -874,13 +880,10 @@ __device__ bool coupled_halo(const CoupledArgs& A, const double* x)
     const int lane = threadIdx.x & 31;
     const CommDev& c = A.comm;
     WindowHeader* me = win_hdr(c, c.rank);
-    unsigned long long epoch = 0;
-    if (lane == 0) epoch = me->haloEpoch + 1;
-    epoch = __shfl_sync(0xffffffffu, epoch, 0);
-    const int par = (int)(epoch & 1ull);
     __syncwarp();      // x was written by lane 0
     for (int k = 0; k < A.nIfs; k++) {
         const IfaceDev it = A.ifs[k];
+        const int par = (int)((me->haloSent[it.nbrRank] + 1ull) & 1ull);
         double* dst = win_halo(c, it.nbrRank, par, it.nbrInterface);
         for (int i = lane; i < it.n; i += 32) dst[i] = x[A.ifCells[it.offset + i]];
     }
@@ -888,14 +891,25 @@ __device__ bool coupled_halo(const CoupledArgs& A, const double* x)
     __syncwarp();
     bool ok = true;
     if (lane == 0) {
-        me->haloEpoch = epoch;
-        for (int k = 0; k < A.nIfs; k++) st_release_sys(&win_hdr(c, A.ifs[k].nbrRank)->haloSeq[par][c.rank], epoch);
-        for (int k = 0; k < A.nIfs && ok; k++) ok = wait_epoch(&me->haloSeq[par][A.ifs[k].nbrRank], epoch, c.timeoutCycles);
+        for (int k = 0; k < A.nIfs; k++) {
+            const int r = A.ifs[k].nbrRank;
+            bool first = true;
+            for (int j = 0; j < k; j++) first = first && A.ifs[j].nbrRank != r;
+            if (!first) continue;
+            const unsigned long long epoch = me->haloSent[r] + 1ull;
+            me->haloSent[r] = epoch;
+            st_release_sys(&win_hdr(c, r)->haloSeq[(int)(epoch & 1ull)][c.rank], epoch);
+        }
+        for (int k = 0; k < A.nIfs && ok; k++) {
+            const unsigned long long epoch = me->haloSent[A.ifs[k].nbrRank];
+            ok = wait_epoch(&me->haloSeq[(int)(epoch & 1ull)][A.ifs[k].nbrRank], epoch, c.timeoutCycles);
+        }
     }
     ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
     if (!ok) return false;
     for (int k = 0; k < A.nIfs; k++) {
         const IfaceDev it = A.ifs[k];
+        const int par = (int)(me->haloSent[it.nbrRank] & 1ull);
         const double* src = win_halo(c, c.rank, par, k);
         for (int i = lane; i < it.n; i += 32) A.recv[it.offset + i] = ld_volatile_f64(src + i);
     }
