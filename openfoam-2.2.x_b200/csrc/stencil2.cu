@@ -1560,7 +1560,7 @@ int pick_M4(int nz)
     const char* e = getenv("LDU_STENCIL_M");
     if (e) {
         const int m = atoi(e);
-        if (m == 2 || m == 4 || m == 8 || m == 16) return m;    // 16: chains of 16 warps with ONE plane each
+        if (m == 2 || m == 4 || m == 8) return m;
     }
     return nz >= 32 ? 8 : nz >= 8 ? 4 : 2;
 }
@@ -1594,14 +1594,15 @@ int state2(ldu_matrix* m, State2** out)
         const bool v3 = gen >= 3;
         s->gen = gen;
         s->M4 = gen == 4 ? pick_M4(b.nz) : 0;
-        s->W = gen == 4 ? (s->M4 == 16 ? 16 : 2 * s->M4) : v3 ? pick_W3(b.nz) : pick_W(b.nz);
+        s->W = gen == 4 ? 2 * s->M4 : v3 ? pick_W3(b.nz) : pick_W(b.nz);
         b.nKg = (b.nz + s->W - 1) / s->W;
         // the two planes of a chain warp run the same step in a tick (blocked layout, see tile_row); LDU_STENCIL_BLK=1:
         // every plane one tick behind the plane below, as in the third generation
         b.blk = 1;
-        if (gen == 4 && s->M4 != 16) {
+        if (gen == 4) {
+            // the unblocked layout is kept (and tested) for chains of 8 warps only
             const char* be = getenv("LDU_STENCIL_BLK");
-            b.blk = (be && atoi(be) == 1) ? 1 : 2;
+            b.blk = (be && atoi(be) == 1 && s->M4 == 8) ? 1 : 2;
         }
         b.W3 = v3 ? s->W : 0;
         b.ticks = b.steps + s->W / b.blk - 1;
@@ -1875,13 +1876,10 @@ static int apply_core(ldu_matrix* m, const double* rD, const double* coefF, cons
     a.gK = s->gK;
     a.gJ = s->gJ;
     a.ticket = s->ticket;
-    if (s->gen == 4 && s->M4 == 16) LDU_TRY((launch_sweeps4<1, 16, false>(m, s, a, P)));
-    else if (s->gen == 4 && s->M4 == 8 && s->b.blk == 2) LDU_TRY((launch_sweeps4<2, 8, true>(m, s, a, P)));
-    else if (s->gen == 4 && s->M4 == 4 && s->b.blk == 2) LDU_TRY((launch_sweeps4<2, 4, true>(m, s, a, P)));
-    else if (s->gen == 4 && s->b.blk == 2) LDU_TRY((launch_sweeps4<2, 2, true>(m, s, a, P)));
-    else if (s->gen == 4 && s->M4 == 8) LDU_TRY((launch_sweeps4<2, 8, false>(m, s, a, P)));
-    else if (s->gen == 4 && s->M4 == 4) LDU_TRY((launch_sweeps4<2, 4, false>(m, s, a, P)));
-    else if (s->gen == 4) LDU_TRY((launch_sweeps4<2, 2, false>(m, s, a, P)));
+    if (s->gen == 4 && s->M4 == 8 && s->b.blk == 2) LDU_TRY((launch_sweeps4<2, 8, true>(m, s, a, P)));
+    else if (s->gen == 4 && s->M4 == 4) LDU_TRY((launch_sweeps4<2, 4, true>(m, s, a, P)));
+    else if (s->gen == 4 && s->M4 == 2) LDU_TRY((launch_sweeps4<2, 2, true>(m, s, a, P)));
+    else if (s->gen == 4) LDU_TRY((launch_sweeps4<2, 8, false>(m, s, a, P)));
     else if (s->b.W3 == 16) LDU_TRY(launch_sweeps3<16>(m, s, a, P));
     else if (s->b.W3 == 12) LDU_TRY(launch_sweeps3<12>(m, s, a, P));
     else if (s->b.W3 == 8) LDU_TRY(launch_sweeps3<8>(m, s, a, P));
