@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "epilogue.cuh"
+#include "comm.cuh"
 #include "reduce.cuh"
 
 namespace ldu {
@@ -446,6 +447,57 @@ __global__ void __launch_bounds__(kBlock) interface_kernel(int nBRows, const int
     result[c] = acc;
 }
 
+// updateMatrixInterfaces in ONE kernel: every block waits for the neighbours' halos of the exchange this rank has
+// just sent its own for (what halo_recv_kernel does), then the coupled rows read the neighbour values straight from
+// the window slots (what halo_recv_kernel copied into the receive buffer for interface_kernel<0>): one launch and one
+// pass over the halo less per Amul / residual / Gauss-Seidel boundary update.  Same terms in the same order.
+constexpr int kFusedIfs = 32;
+__global__ void __launch_bounds__(kBlock) interface_wait_kernel(CommDev c, const IfaceDev* __restrict__ ifs, int nIfs,
+                                                                 int nBRows, const int* __restrict__ bRowCell,
+                                                                 const int* __restrict__ bRowStart,
+                                                                 const int* __restrict__ bEntry,
+                                                                 const double* __restrict__ coeff, double sign,
+                                                                 double* __restrict__ result, SolverScalars* S,
+                                                                 bool guarded)
+{
+    if (guarded && S->done) return;
+    WindowHeader* me = win_hdr(c, c.rank);
+    __shared__ bool ok;
+    __shared__ const double* slot[kFusedIfs];     // window slot of interface q, shifted by its offset
+    __shared__ int first[kFusedIfs + 1];
+    if (threadIdx.x == 0) {
+        ok = true;
+        for (int k = 0; k < nIfs && ok; k++) {
+            const unsigned long long epoch = me->haloSent[ifs[k].nbrRank];
+            ok = wait_epoch(&me->haloSeq[(int)(epoch & 1ull)][ifs[k].nbrRank], epoch, c.timeoutCycles);
+        }
+        if (!ok) {
+            S->commError = 1;
+            S->done = 1;
+        }
+    }
+    if (threadIdx.x < nIfs) {
+        const IfaceDev it = ifs[threadIdx.x];
+        const int par = (int)(me->haloSent[it.nbrRank] & 1ull);
+        slot[threadIdx.x] = win_halo(c, c.rank, par, threadIdx.x) - it.offset;
+        first[threadIdx.x] = it.offset;
+        if (threadIdx.x == nIfs - 1) first[nIfs] = it.offset + it.n;
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int r = blockIdx.x * kBlock + threadIdx.x;
+    if (r >= nBRows) return;
+    const int cell = bRowCell[r];
+    double acc = result[cell];
+    for (int e = bRowStart[r]; e < bRowStart[r + 1]; e++) {
+        const int k = bEntry[e];
+        int q = 0;
+        while (q + 1 < nIfs && k >= first[q + 1]) q++;
+        acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(sign, coeff[k]), ld_volatile_f64(slot[q] + k)));
+    }
+    result[cell] = acc;
+}
+
 template <int MODE>
 static int launch_rows(ldu_matrix* m, const RowView& v, double* y, const double* x, const double* b,
                        bool guarded)
@@ -538,9 +590,20 @@ static int launch_rows(ldu_matrix* m, const RowView& v, double* y, const double*
 static int k_interfaces_finish(ldu_matrix* m, double* result, int whichCoeffs, double sign, bool guarded)
 {
     if (!m->nIfFaces) return LDU_OK;
-    LDU_TRY(comm_halo_recv(m, guarded));
     const double* coeff = whichCoeffs ? m->d_int : m->d_bou;
     const int grid = (m->nBRows + kBlock - 1) / kBlock;
+    static const bool fusedOff = getenv("LDU_IF_FUSED") && getenv("LDU_IF_FUSED")[0] == '0';
+    if (!fusedOff && (int)m->ifs.size() <= kFusedIfs) {
+        const IfaceDev* tab = nullptr;
+        LDU_TRY(comm_halo_table(m, &tab));
+        interface_wait_kernel<<<grid, kBlock, 0, m->ctx->stream>>>(comm_dev(m->ctx), tab, (int)m->ifs.size(), m->nBRows,
+                                                                  m->d_bRowCell, m->d_bRowStart, m->d_bEntry, coeff, sign,
+                                                                  result, m->d_scalars, guarded);
+        count_launch();
+        LDU_CUDA(cudaGetLastError());
+        return LDU_OK;
+    }
+    LDU_TRY(comm_halo_recv(m, guarded));
     interface_kernel<0><<<grid, kBlock, 0, m->ctx->stream>>>(m->nBRows, m->d_bRowCell, m->d_bRowStart,
                                                             m->d_bEntry, coeff, m->d_recv, sign, result,
                                                             guarded ? m->d_scalars : nullptr);
