@@ -26,113 +26,12 @@
 #include "epilogue.cuh"
 #include "reduce.cuh"
 #include "sweeps.h"
+#include "gamg_host.h"
 
 namespace ldu {
 
 constexpr int kMaxLevels = 50;             // GAMGAgglomeration.C:74
-constexpr double kScalarGreat = 1.0e+15;   // primitives/Scalar/doubleScalar/doubleScalar.H:54
 constexpr double kVSmallG = 1.0e-300;
-
-// ---------------------------------------------------------------------------
-// host: one level of pairwise clustering
-// ---------------------------------------------------------------------------
-static std::vector<int> pair_cluster(int nFine, const std::vector<int>& lower, const std::vector<int>& upper,
-                                     const std::vector<double>& w, int& nCoarse)
-{
-    const int nFaces = (int)lower.size();
-    // faces around each cell: first the faces where the cell is the neighbour,
-    // then those where it is the owner (the order the reference scans them in)
-    std::vector<int> start(nFine + 1, 0);
-    for (int f = 0; f < nFaces; f++) {
-        start[upper[f] + 1]++;
-        start[lower[f] + 1]++;
-    }
-    for (int c = 0; c < nFine; c++) start[c + 1] += start[c];
-    std::vector<int> cellFaces(2 * (size_t)nFaces), fill(start.begin(), start.end() - 1);
-    for (int f = 0; f < nFaces; f++) cellFaces[fill[upper[f]]++] = f;
-    for (int f = 0; f < nFaces; f++) cellFaces[fill[lower[f]]++] = f;
-
-    std::vector<int> cmap(nFine, -1);
-    nCoarse = 0;
-    for (int c = 0; c < nFine; c++) {
-        if (cmap[c] >= 0) continue;
-        int match = -1;
-        double best = -kScalarGreat;
-        for (int k = start[c]; k < start[c + 1]; k++) {
-            const int f = cellFaces[k];
-            if (cmap[upper[f]] < 0 && cmap[lower[f]] < 0 && w[f] > best) {
-                match = f;
-                best = w[f];
-            }
-        }
-        if (match >= 0) {  // new pair
-            cmap[upper[match]] = nCoarse;
-            cmap[lower[match]] = nCoarse;
-            nCoarse++;
-            continue;
-        }
-        // no free neighbour: join the cluster across the heaviest face
-        int cmatch = -1;
-        best = -kScalarGreat;
-        for (int k = start[c]; k < start[c + 1]; k++) {
-            const int f = cellFaces[k];
-            if (w[f] > best) {
-                cmatch = f;
-                best = w[f];
-            }
-        }
-        if (cmatch >= 0) cmap[c] = std::max(cmap[upper[cmatch]], cmap[lower[cmatch]]);
-    }
-    for (int c = 0; c < nFine; c++)
-        if (cmap[c] < 0) cmap[c] = nCoarse++;
-    // the reference reverses the cluster numbering (pairGAMGAgglomerate.C:186-195)
-    for (int c = 0; c < nFine; c++) cmap[c] = nCoarse - 1 - cmap[c];
-    return cmap;
-}
-
-// host: coarse owner/neighbour and the fine-face -> coarse-face map
-static void coarse_addressing(int nCoarse, const std::vector<int>& lower, const std::vector<int>& upper,
-                              const std::vector<int>& cmap, std::vector<int>& faceMap,
-                              std::vector<int>& cOwner, std::vector<int>& cNeighbour)
-{
-    const int nFaces = (int)lower.size();
-    faceMap.assign(nFaces, 0);
-    // per coarse owner: (neighbour, provisional face id) in discovery order
-    std::vector<std::vector<std::pair<int, int>>> found(nCoarse);
-    int nCoarseFaces = 0;
-    for (int f = 0; f < nFaces; f++) {
-        const int a = cmap[upper[f]], b = cmap[lower[f]];
-        if (a == b) {
-            faceMap[f] = -(a + 1);  // interior to a coarse cell
-            continue;
-        }
-        const int own = std::min(a, b), nei = std::max(a, b);
-        int id = -1;
-        for (const auto& e : found[own])
-            if (e.first == nei) {
-                id = e.second;
-                break;
-            }
-        if (id < 0) {
-            id = nCoarseFaces++;
-            found[own].push_back(std::make_pair(nei, id));
-        }
-        faceMap[f] = id;
-    }
-    // renumber owner-major, discovery order within an owner (GAMGAgglomerateLduAddressing.C:158-185)
-    cOwner.resize(nCoarseFaces);
-    cNeighbour.resize(nCoarseFaces);
-    std::vector<int> renum(nCoarseFaces);
-    int cf = 0;
-    for (int c = 0; c < nCoarse; c++)
-        for (const auto& e : found[c]) {
-            cOwner[cf] = c;
-            cNeighbour[cf] = e.first;
-            renum[e.second] = cf++;
-        }
-    for (int f = 0; f < nFaces; f++)
-        if (faceMap[f] >= 0) faceMap[f] = renum[faceMap[f]];
-}
 
 template <class T>
 static int to_device(ldu_context* ctx, T** d, const std::vector<T>& h)
