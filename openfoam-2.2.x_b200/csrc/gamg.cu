@@ -191,29 +191,6 @@ static int build_level_device(ldu_matrix* fine, const HostLevel& H, GamgLevel** 
     return LDU_OK;
 }
 
-// coarse processor interface of one pairing step (processorGAMGInterface.C:47-126)
-static void agglomerate_interface(int myRank, int nbrRank, const std::vector<int>& local,
-                                  const std::vector<int>& nbr, std::vector<int>& faceCells,
-                                  std::vector<int>& faceRestrict)
-{
-    std::map<std::pair<int, int>, int> seen;
-    faceCells.clear();
-    faceRestrict.resize(local.size());
-    for (size_t i = 0; i < local.size(); i++) {
-        const std::pair<int, int> key = (myRank < nbrRank) ? std::make_pair(local[i], nbr[i])
-                                                           : std::make_pair(nbr[i], local[i]);
-        auto it = seen.find(key);
-        if (it == seen.end()) {
-            const int id = (int)faceCells.size();
-            seen.emplace(key, id);
-            faceCells.push_back(local[i]);
-            faceRestrict[i] = id;
-        } else {
-            faceRestrict[i] = it->second;
-        }
-    }
-}
-
 // a matrix-less carrier for the interfaces of the mesh currently being paired:
 // lets the restrict-map exchange reuse the halo kernels
 static int make_carrier(ldu_context* ctx, int nCells, const std::vector<std::vector<int>>& ifCells,

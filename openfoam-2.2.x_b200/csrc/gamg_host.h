@@ -5,6 +5,7 @@
 #pragma once
 
 #include <algorithm>
+#include <map>
 #include <utility>
 #include <vector>
 
@@ -117,6 +118,31 @@ inline void coarse_addressing(int nCoarse, const std::vector<int>& lower, const 
         }
     for (int f = 0; f < nFaces; f++)
         if (faceMap[f] >= 0) faceMap[f] = renum[faceMap[f]];
+}
+
+// coarse processor interface of one pairing step (processorGAMGInterface.C:47-126): the faces of the interface are
+// merged by the pair (coarse cell here, coarse cell there), keyed from the side of the lower rank so that both
+// sides number the coarse faces alike; local / nbr = the coarse cell of each fine face on this side / the other side
+inline void agglomerate_interface(int myRank, int nbrRank, const std::vector<int>& local,
+                                  const std::vector<int>& nbr, std::vector<int>& faceCells,
+                                  std::vector<int>& faceRestrict)
+{
+    std::map<std::pair<int, int>, int> seen;
+    faceCells.clear();
+    faceRestrict.resize(local.size());
+    for (size_t i = 0; i < local.size(); i++) {
+        const std::pair<int, int> key = (myRank < nbrRank) ? std::make_pair(local[i], nbr[i])
+                                                           : std::make_pair(nbr[i], local[i]);
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            const int id = (int)faceCells.size();
+            seen.emplace(key, id);
+            faceCells.push_back(local[i]);
+            faceRestrict[i] = id;
+        } else {
+            faceRestrict[i] = it->second;
+        }
+    }
 }
 
 }  // namespace ldu

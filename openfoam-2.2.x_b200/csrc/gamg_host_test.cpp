@@ -78,4 +78,16 @@ int ldu_hosttest_coarse_addressing(int which, int nCoarse, int nFaces, const int
     std::memcpy(cNeighbourOut, cNeighbour.data(), cNeighbour.size() * sizeof(int));
     return (int)cOwner.size();
 }
+
+// faceCellsOut / faceRestrictOut sized n.  Returns the number of coarse interface faces.
+int ldu_hosttest_agglomerate_interface(int myRank, int nbrRank, int n, const int* local, const int* nbr,
+                                       int* faceCellsOut, int* faceRestrictOut)
+{
+    std::vector<int> faceCells, faceRestrict;
+    ldu::agglomerate_interface(myRank, nbrRank, std::vector<int>(local, local + n), std::vector<int>(nbr, nbr + n),
+                               faceCells, faceRestrict);
+    std::memcpy(faceCellsOut, faceCells.data(), faceCells.size() * sizeof(int));
+    std::memcpy(faceRestrictOut, faceRestrict.data(), faceRestrict.size() * sizeof(int));
+    return (int)faceCells.size();
+}
 }

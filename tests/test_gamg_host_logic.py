@@ -27,6 +27,8 @@ def lib():
     L.ldu_hosttest_pair_cluster.restype = C.c_int
     L.ldu_hosttest_coarse_addressing.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, ip, ip, ip]
     L.ldu_hosttest_coarse_addressing.restype = C.c_int
+    L.ldu_hosttest_agglomerate_interface.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, ip]
+    L.ldu_hosttest_agglomerate_interface.restype = C.c_int
     return L
 
 
@@ -102,3 +104,51 @@ def test_flat_coarse_addressing_equals_the_straightforward_one(lib, seed):
     want = coarse_addressing(lib, 1, nc, lower, upper, cmap)
     for g, wv in zip(got, want):
         assert np.array_equal(g, wv)
+
+
+def agglomerate_interface(L, my_rank, nbr_rank, local, nbr):
+    local, nbr = np.ascontiguousarray(local, np.int32), np.ascontiguousarray(nbr, np.int32)
+    fc, fr = np.empty(max(local.size, 1), np.int32), np.empty(max(local.size, 1), np.int32)
+    n = L.ldu_hosttest_agglomerate_interface(my_rank, nbr_rank, local.size, _ip(local), _ip(nbr), _ip(fc), _ip(fr))
+    return fc[:n].copy(), fr[:local.size].copy()
+
+
+@pytest.mark.skipif(not O.ref_par_available(), reason="ref_driver_par not built")
+@pytest.mark.parametrize("n_regions,partition", [(2, "slab"), (3, "slab"), (3, "random")])
+def test_coupled_levels_equal_the_compiled_reference(lib, n_regions, partition):
+    """Several regions: clustering per region, and the coarse processor interfaces formed from the neighbour's
+    restrict map (what gamg.cu exchanges through the halo kernels), against GAMGAgglomeration::New of the
+    unmodified reference running one process per region."""
+    s, regs = cases.regions("box12_var", n_regions, partition)
+    ctl = dict(solver="GAMG", smoother="GaussSeidel", nCellsInCoarsestLevel=4, mergeLevels=1,
+               agglomerator="faceAreaPair")
+    ref = O.ref_agglom_full_par(regs, cases.ref_controls(ctl))
+    n_lev = len(ref[0])
+    assert n_lev >= 2 and all(len(r) == n_lev for r in ref)
+    cur = [dict(n=r["nCells"], lower=r["lower"], upper=r["upper"], w=np.asarray(r["faceWeights"], float),
+                ifCells=[it["faceCells"] for it in r["interfaces"]]) for r in regs]
+    for lev in range(n_lev):
+        cmaps = []
+        for r, c in enumerate(cur):
+            nc, cmap = pair_cluster(lib, c["n"], c["lower"], c["upper"], c["w"])
+            assert nc == ref[r][lev]["nCoarse"] and np.array_equal(cmap, ref[r][lev]["restrict"])
+            cmaps.append(cmap)
+        nxt = []
+        for r, c in enumerate(cur):
+            fm, co, cn = coarse_addressing(lib, 0, ref[r][lev]["nCoarse"], c["lower"], c["upper"], cmaps[r])
+            assert np.array_equal(co, ref[r][lev]["lower"]) and np.array_equal(cn, ref[r][lev]["upper"])
+            assert np.array_equal(fm, ref[r][lev]["faceRestrict"])
+            if_cells = []
+            for p, it in enumerate(regs[r]["interfaces"]):
+                q, pq = it["nbrRegion"], it["nbrInterface"]
+                local = cmaps[r][c["ifCells"][p]]
+                nbr = cmaps[q][cur[q]["ifCells"][pq]]          # the halo exchange of the restrict map
+                fc, fr = agglomerate_interface(lib, r, q, local, nbr)
+                assert np.array_equal(fc, ref[r][lev]["ifCells"][p])
+                assert np.array_equal(fr, ref[r][lev]["ifRestrict"][p])
+                if_cells.append(fc)
+            cw = np.zeros(co.size)
+            keep = fm >= 0
+            np.add.at(cw, fm[keep], c["w"][keep])
+            nxt.append(dict(n=ref[r][lev]["nCoarse"], lower=co, upper=cn, w=cw, ifCells=if_cells))
+        cur = nxt
