@@ -750,6 +750,8 @@ __device__ bool coupled_halo_ll(const CoupledArgs& A, const double* x)
     return ok;
 }
 
+// the fall-back for interfaces with more than kLLFaces faces (a large nCellsInCoarsestLevel): window slots, system
+// fence, epoch flags -- the protocol of halo_put_kernel / interface_wait_kernel run by the one warp
 __device__ bool coupled_halo(const CoupledArgs& A, const double* x)
 {
     if (A.nIfs == 0) return true;
@@ -782,6 +784,7 @@ __device__ bool coupled_halo(const CoupledArgs& A, const double* x)
         }
     }
     ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+    __syncwarp();      // lane 0 has advanced haloSent
     if (!ok) return false;
     for (int k = 0; k < A.nIfs; k++) {
         const IfaceDev it = A.ifs[k];
