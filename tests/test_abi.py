@@ -103,3 +103,21 @@ def test_direct_solve_coarsest_is_refused():
     with pytest.raises(ldub200.LduError, match="directSolveCoarsest"):
         ldub200.make_controls(dict(solver="GAMG", smoother="GaussSeidel", directSolveCoarsest=True))
     ldub200.make_controls(dict(solver="GAMG", smoother="GaussSeidel", directSolveCoarsest=False))
+
+
+def test_environment_switches_are_documented():
+    """every LDU_* variable the library or the plug-in reads is listed in INTEGRATION.md section 4, and the table
+    lists nothing that no longer exists"""
+    import re
+    root = Path(__file__).resolve().parent.parent
+    src = ""
+    for pat in ("openfoam-2.2.x_b200/csrc/*.cu", "openfoam-2.2.x_b200/csrc/*.cuh", "openfoam-2.2.x_b200/csrc/*.h",
+                "openfoam-2.2.x_b200/foam/*.C"):
+        for f in root.glob(pat):
+            src += f.read_text()
+    read = set(re.findall(r'getenv\("(LDU_[A-Z0-9_]+)"\)', src))
+    doc = (root / "INTEGRATION.md").read_text()
+    table = doc[doc.index("## 4. Environment switches"):]
+    listed = set(re.findall(r"`(LDU_[A-Z0-9_]+)", table))
+    assert read - listed == set(), f"undocumented: {sorted(read - listed)}"
+    assert listed - read == set(), f"documented but not read anywhere: {sorted(listed - read)}"
